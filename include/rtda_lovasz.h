@@ -1,0 +1,120 @@
+/* rtda_lovasz.h - C ABI of the B200-native Lovasz-Softmax / confusion-matrix hot path.
+ *
+ * The reference (arman-rn/RTDA-SemanticSegmentation) is pure Python and has no
+ * FFI of its own; these entry points are what a binding of its hot path binds:
+ *
+ *   rtda_lovasz_fwd / rtda_lovasz_bwd   replace LovaszSoftmax.forward
+ *       (losses/lovasz_loss.py:185-200: prob_flatten :93-120, lovasz_softmax_flat
+ *       :122-183, lovasz_grad :47-70, mean :19-44) and its autograd backward,
+ *       as called from train_lovasz.py:102,124,282 and :108,129,292.
+ *   rtda_confusion_accumulate           replaces the validation.py:98-109 slice
+ *       (ignore filter + utils.py:62-89 fast_hist + `hist +=`).
+ *   rtda_confusion_argmax_accumulate    the same fused with validation.py:95
+ *       (argmax over the class dimension of the logits).
+ *
+ * Conventions (all functions):
+ *   - return 0 on success, > 0 a cudaError_t, < 0 an argument error (RTDA_E_*);
+ *   - no allocation, no host synchronisation, no global state besides a
+ *     per-device attribute cache: every buffer (workspace included) is owned by
+ *     the caller, all work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*), so the calls are re-entrant per (device, stream);
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - probabilities / gradients are fp32 NCHW contiguous, 16-byte aligned.
+ *
+ * Label element types (`label_kind`): RTDA_LABEL_I64 is what the reference's
+ * callers pass (`labels.long()`, train_lovasz.py:66); U8 / I32 are fast paths
+ * for the dataset-native masks (datasets/cityscapes.py:73-82).
+ */
+#ifndef RTDA_LOVASZ_H
+#define RTDA_LOVASZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTDA_ABI_VERSION 1
+
+#define RTDA_E_ARG (-1)        /* null pointer / non-positive size */
+#define RTDA_E_RANGE (-2)      /* a size exceeds what the kernels index (see below) */
+#define RTDA_E_WORKSPACE (-3)  /* ws_bytes smaller than rtda_lovasz_workspace_bytes */
+#define RTDA_E_ALIGN (-4)      /* a pointer is not 16-byte aligned */
+
+#define RTDA_LABEL_I64 0
+#define RTDA_LABEL_U8 1
+#define RTDA_LABEL_I32 2
+
+#define RTDA_MAX_CLASSES 44        /* Lovasz: per-class digit histograms live in shared memory */
+#define RTDA_MAX_SEGMENT (1 << 30) /* Lovasz: pixels per sort segment (B*H*W global, H*W per image) */
+
+/* ABI version of the loaded library (== RTDA_ABI_VERSION it was built with). */
+int rtda_version(void);
+
+/* Static string for a return code of this library (cudaGetErrorString for > 0). */
+const char *rtda_error_string(int code);
+
+/* ---- Lovasz-Softmax -------------------------------------------------------
+ * Segments: per_image == 0 -> one sort problem per class over all B*HW pixels
+ * (what LovaszSoftmax.forward computes, lovasz_loss.py:197-199); per_image != 0
+ * -> one per (image, class), averaged over images with the reference's `mean`
+ * (the composition SURVEY.md 0.2 defines).  G = per_image ? B : 1 groups.
+ *
+ * Pixels whose label equals `ignore` (when has_ignore) or lies outside [0, C)
+ * take no part (lovasz_loss.py:157-161); the number of out-of-range labels is
+ * added to *label_errors so a caller can raise the reference's IndexError.
+ */
+
+/* Bytes of scratch rtda_lovasz_fwd needs for this shape. */
+int rtda_lovasz_workspace_bytes(int64_t B, int C, int64_t HW, int per_image, size_t *bytes);
+
+/* Debug / test aid: byte offsets of the regions inside the workspace, in the order
+ * {hist, fghist, tickets, desc32, desc64, zero_end, base, fgbase, seg_fg, codes,
+ *  partial, buf_a, buf_b, total, segments S, tiles per segment T}.  offsets[16]. */
+int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t *offsets);
+
+/* Forward.  Outputs:
+ *   unit_grad     [G][C][n] fp32, n = B*HW/G: d(sum of present class losses of the
+ *                 group)/d(probas) for grad_out = 1 before the 1/K and 1/G factors,
+ *                 i.e. -g_rank * sgn(fg - p); rows of absent classes are NOT written.
+ *                 May be NULL (loss only, e.g. under torch.no_grad()).
+ *   loss          [1]    fp32  the scalar loss (0 when nothing is valid)
+ *   class_loss    [G][C] fp32  per-class Lovasz losses (0 where absent)
+ *   class_present [G][C] i32   1 where the class has a valid foreground pixel
+ *   n_present     [G]    i32   K of each group
+ *   group_loss    [G]    fp32  loss of each group (image); may be NULL
+ *   label_errors  [1]    i32   += number of labels outside [0,C) and != ignore
+ */
+int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
+                    int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
+                    void *ws, size_t ws_bytes,
+                    float *unit_grad, float *loss, float *class_loss, int32_t *class_present,
+                    int32_t *n_present, float *group_loss, int32_t *label_errors, void *stream);
+
+/* Backward: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) for present
+ * classes, 0 elsewhere (the autograd of lovasz_loss.py:19-44,180); every element
+ * of grad_probas [B][C][HW] is written.  grad_out is a DEVICE scalar. */
+int rtda_lovasz_bwd(const float *grad_out, const float *unit_grad, const int32_t *class_present,
+                    const int32_t *n_present, int64_t B, int C, int64_t HW, int per_image,
+                    float *grad_probas, void *stream);
+
+/* ---- Confusion matrix -----------------------------------------------------
+ * hist[t * n_class + p] += 1 for every pixel with label t != ignore,
+ * 0 <= t < n_class and 0 <= p < n_class (validation.py:102-107 + utils.py:78-87).
+ * hist is int64 [n_class * n_class] and is accumulated into, not overwritten.
+ */
+int rtda_confusion_accumulate(const void *labels, int label_kind, const void *preds, int pred_kind,
+                              int64_t n, int n_class, int64_t ignore, int has_ignore,
+                              int64_t *hist, void *stream);
+
+/* Same, with the prediction taken as argmax over the class dimension of fp32
+ * NCHW logits [B][n_class][HW] (first maximum wins, like torch.argmax). */
+int rtda_confusion_argmax_accumulate(const float *logits, const void *labels, int label_kind,
+                                     int64_t B, int n_class, int64_t HW, int64_t ignore, int has_ignore,
+                                     int64_t *hist, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTDA_LOVASZ_H */

@@ -1,0 +1,245 @@
+// Confusion-matrix histogram for sm_100a (B200).
+//
+// Replaces the per-batch slice of the reference's validation loop
+// (validation.py:98-109: two D2H copies, ignore filter, utils.py:62-89 fast_hist,
+// `hist +=`) with one pass over device-resident label / prediction maps, and
+// optionally fuses validation.py:95 (argmax over the logits).
+//
+// HBM-bound integer work (16 B/pixel for int64 maps, 2 888 B out).  Real label
+// maps are spatially coherent and mostly predicted right, so nearly all
+// increments land on the n_class diagonal bins: each warp first groups equal
+// bins with match.any and one lane adds the group size to a WARP-PRIVATE
+// shared-memory histogram (no atomics, no same-address serialisation); blocks
+// flush non-zero bins to the int64 matrix with one atomicAdd each.
+#include "common.cuh"
+
+namespace rtda {
+
+constexpr int kCmThreads = 256;
+constexpr int kCmWarps = kCmThreads / 32;
+constexpr int kCmUnroll = 4;
+
+// mode 0: one private histogram per warp; mode 1: one per block (shared atomics);
+// mode 2: no shared histogram (global atomics), for very large n_class.
+template <int MODE>
+__device__ __forceinline__ void cm_add(u32 *sh, int nbins, u32 bin, bool ok, unsigned long long *hist) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 m = __match_any_sync(RTDA_FULL_MASK, ok ? bin : 0xffffffffu);
+    if (ok && lane == (u32)(__ffs(m) - 1)) {
+        const u32 cnt = __popc(m);
+        if (MODE == 0) sh[warp * nbins + bin] += cnt;
+        else if (MODE == 1) atomicAdd(&sh[bin], cnt);
+        else atomicAdd(&hist[bin], (unsigned long long)cnt);
+    }
+    if (MODE == 0) __syncwarp();
+}
+
+template <int MODE>
+__device__ __forceinline__ void cm_flush(u32 *sh, int nbins, unsigned long long *hist) {
+    if (MODE == 2) return;
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += kCmThreads) {
+        u32 s = 0;
+        if (MODE == 0) {
+#pragma unroll
+            for (int w = 0; w < kCmWarps; ++w) s += sh[w * nbins + b];
+        } else {
+            s = sh[b];
+        }
+        if (s) atomicAdd(&hist[b], (unsigned long long)s);
+    }
+}
+
+template <typename LabelT, typename PredT, int MODE>
+__global__ void __launch_bounds__(kCmThreads)
+k_confusion(const LabelT *__restrict__ labels, const PredT *__restrict__ preds, long long n, int n_class,
+            long long ignore, int has_ignore, unsigned long long *__restrict__ hist) {
+    extern __shared__ u32 sh[];
+    const int nbins = n_class * n_class;
+    if (MODE != 2) {
+        const int words = (MODE == 0 ? kCmWarps : 1) * nbins;
+        for (int i = threadIdx.x; i < words; i += kCmThreads) sh[i] = 0;
+        __syncthreads();
+    }
+    const long long stride = (long long)gridDim.x * kCmThreads * kCmUnroll;
+    // every lane of a warp runs the same number of iterations (match.any needs the full warp)
+    for (long long base = (long long)blockIdx.x * kCmThreads * kCmUnroll; base < n; base += stride) {
+        long long t[kCmUnroll], p[kCmUnroll];
+        bool in[kCmUnroll];
+#pragma unroll
+        for (int k = 0; k < kCmUnroll; ++k) {
+            const long long i = base + (long long)k * kCmThreads + threadIdx.x;
+            in[k] = i < n;
+            t[k] = in[k] ? (long long)labels[i] : -1;
+            p[k] = in[k] ? (long long)preds[i] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kCmUnroll; ++k) {
+            const bool ok = in[k] && !(has_ignore && t[k] == ignore) &&      // validation.py:102
+                            t[k] >= 0 && t[k] < n_class && p[k] >= 0 && p[k] < n_class;  // utils.py:78-83
+            const u32 bin = ok ? (u32)(t[k] * n_class + p[k]) : 0u;          // utils.py:84-87
+            cm_add<MODE>(sh, nbins, bin, ok, hist);
+        }
+    }
+    cm_flush<MODE>(sh, nbins, hist);
+}
+
+// Fused validation.py:95 (argmax over classes, first maximum wins) + the histogram.
+template <typename LabelT, int MODE>
+__global__ void __launch_bounds__(kCmThreads)
+k_confusion_argmax(const float *__restrict__ logits, const LabelT *__restrict__ labels, long long B,
+                   int n_class, long long HW, long long ignore, int has_ignore,
+                   unsigned long long *__restrict__ hist) {
+    extern __shared__ u32 sh[];
+    const int nbins = n_class * n_class;
+    if (MODE != 2) {
+        const int words = (MODE == 0 ? kCmWarps : 1) * nbins;
+        for (int i = threadIdx.x; i < words; i += kCmThreads) sh[i] = 0;
+        __syncthreads();
+    }
+    const long long n = B * HW;
+    const long long stride = (long long)gridDim.x * kCmThreads;
+    for (long long base = (long long)blockIdx.x * kCmThreads; base < n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool in = i < n;
+        long long t = -1;
+        int arg = 0;
+        if (in) {
+            t = (long long)labels[i];
+            const long long b = i / HW, hw = i - b * HW;
+            const float *px = logits + (size_t)(b * n_class) * HW + hw;
+            float best = ld_stream_f1(px);
+            for (int c = 1; c < n_class; ++c) {
+                const float v = ld_stream_f1(px + (size_t)c * HW);
+                if (v > best || (v != v && best == best)) { best = v; arg = c; }  // NaN counts as maximal, like torch
+            }
+        }
+        const bool ok = in && !(has_ignore && t == ignore) && t >= 0 && t < n_class;
+        const u32 bin = ok ? (u32)(t * n_class + arg) : 0u;
+        cm_add<MODE>(sh, nbins, bin, ok, hist);
+    }
+    cm_flush<MODE>(sh, nbins, hist);
+}
+
+static int cm_mode(int n_class, size_t *smem) {
+    const size_t nb = (size_t)n_class * n_class * sizeof(u32);
+    if (nb * kCmWarps <= 64 * 1024) { *smem = nb * kCmWarps; return 0; }
+    if (nb <= 160 * 1024) { *smem = nb; return 1; }
+    *smem = 0;
+    return 2;
+}
+
+template <typename LabelT, typename PredT>
+static int launch_confusion(const void *labels, const void *preds, long long n, int n_class, long long ignore,
+                            int has_ignore, int64_t *hist, cudaStream_t st) {
+    size_t smem = 0;
+    const int mode = cm_mode(n_class, &smem);
+    long long grid = (n + kCmThreads * kCmUnroll - 1) / (kCmThreads * kCmUnroll);
+    const long long cap = 8ll * sm_count();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    auto *h = reinterpret_cast<unsigned long long *>(hist);
+    const LabelT *l = (const LabelT *)labels;
+    const PredT *p = (const PredT *)preds;
+    if (mode == 0) {
+        if (smem > 48 * 1024)
+            RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion<LabelT, PredT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_confusion<LabelT, PredT, 0><<<(unsigned)grid, kCmThreads, smem, st>>>(l, p, n, n_class, ignore, has_ignore, h);
+    } else if (mode == 1) {
+        if (smem > 48 * 1024)
+            RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion<LabelT, PredT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_confusion<LabelT, PredT, 1><<<(unsigned)grid, kCmThreads, smem, st>>>(l, p, n, n_class, ignore, has_ignore, h);
+    } else {
+        k_confusion<LabelT, PredT, 2><<<(unsigned)grid, kCmThreads, 0, st>>>(l, p, n, n_class, ignore, has_ignore, h);
+    }
+    RTDA_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename LabelT>
+static int launch_confusion_pred(const void *labels, const void *preds, int pred_kind, long long n, int n_class,
+                                 long long ignore, int has_ignore, int64_t *hist, cudaStream_t st) {
+    switch (pred_kind) {
+        case RTDA_LABEL_I64: return launch_confusion<LabelT, long long>(labels, preds, n, n_class, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_U8: return launch_confusion<LabelT, unsigned char>(labels, preds, n, n_class, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_I32: return launch_confusion<LabelT, int>(labels, preds, n, n_class, ignore, has_ignore, hist, st);
+    }
+    return RTDA_E_ARG;
+}
+
+template <typename LabelT>
+static int launch_confusion_argmax(const float *logits, const void *labels, long long B, int n_class, long long HW,
+                                   long long ignore, int has_ignore, int64_t *hist, cudaStream_t st) {
+    size_t smem = 0;
+    const int mode = cm_mode(n_class, &smem);
+    const long long n = B * HW;
+    long long grid = (n + kCmThreads - 1) / kCmThreads;
+    const long long cap = 16ll * sm_count();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    auto *h = reinterpret_cast<unsigned long long *>(hist);
+    const LabelT *l = (const LabelT *)labels;
+    if (mode == 0) {
+        if (smem > 48 * 1024)
+            RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion_argmax<LabelT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_confusion_argmax<LabelT, 0><<<(unsigned)grid, kCmThreads, smem, st>>>(logits, l, B, n_class, HW, ignore, has_ignore, h);
+    } else if (mode == 1) {
+        if (smem > 48 * 1024)
+            RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion_argmax<LabelT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_confusion_argmax<LabelT, 1><<<(unsigned)grid, kCmThreads, smem, st>>>(logits, l, B, n_class, HW, ignore, has_ignore, h);
+    } else {
+        k_confusion_argmax<LabelT, 2><<<(unsigned)grid, kCmThreads, 0, st>>>(logits, l, B, n_class, HW, ignore, has_ignore, h);
+    }
+    RTDA_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace rtda
+
+using namespace rtda;
+
+extern "C" int rtda_confusion_accumulate(const void *labels, int label_kind, const void *preds, int pred_kind,
+                                         int64_t n, int n_class, int64_t ignore, int has_ignore,
+                                         int64_t *hist, void *stream) {
+    if (!hist || n < 0 || n_class <= 0) return RTDA_E_ARG;
+    if (n_class > 46340 || n >= (1ll << 40)) return RTDA_E_RANGE;  // n_class^2 must fit int32, block counters u32
+    if (n == 0) return 0;
+    if (!labels || !preds) return RTDA_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (label_kind) {
+        case RTDA_LABEL_I64: return launch_confusion_pred<long long>(labels, preds, pred_kind, n, n_class, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_U8: return launch_confusion_pred<unsigned char>(labels, preds, pred_kind, n, n_class, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_I32: return launch_confusion_pred<int>(labels, preds, pred_kind, n, n_class, ignore, has_ignore, hist, st);
+    }
+    return RTDA_E_ARG;
+}
+
+extern "C" int rtda_confusion_argmax_accumulate(const float *logits, const void *labels, int label_kind,
+                                                int64_t B, int n_class, int64_t HW, int64_t ignore, int has_ignore,
+                                                int64_t *hist, void *stream) {
+    if (!hist || B < 0 || HW < 0 || n_class <= 0) return RTDA_E_ARG;
+    if (n_class > 46340 || B * HW >= (1ll << 40)) return RTDA_E_RANGE;
+    if (B * HW == 0) return 0;
+    if (!logits || !labels) return RTDA_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (label_kind) {
+        case RTDA_LABEL_I64: return launch_confusion_argmax<long long>(logits, labels, B, n_class, HW, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_U8: return launch_confusion_argmax<unsigned char>(logits, labels, B, n_class, HW, ignore, has_ignore, hist, st);
+        case RTDA_LABEL_I32: return launch_confusion_argmax<int>(logits, labels, B, n_class, HW, ignore, has_ignore, hist, st);
+    }
+    return RTDA_E_ARG;
+}
+
+extern "C" int rtda_version(void) { return RTDA_ABI_VERSION; }
+
+extern "C" const char *rtda_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case RTDA_E_ARG: return "rtda: bad argument (null pointer, non-positive size or unknown label kind)";
+        case RTDA_E_RANGE: return "rtda: size out of range (classes > RTDA_MAX_CLASSES or segment >= 2^30 pixels)";
+        case RTDA_E_WORKSPACE: return "rtda: workspace smaller than rtda_lovasz_workspace_bytes()";
+        case RTDA_E_ALIGN: return "rtda: pointer not 16-byte aligned";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "rtda: unknown error";
+}

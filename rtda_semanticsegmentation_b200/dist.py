@@ -1,0 +1,99 @@
+"""Multi-GPU composition of the hot path: one process per GPU, torch.distributed (NCCL).
+
+The reference is single-device (config.py:103) and has no collective.  The path
+shards only where it is naturally partitioned:
+
+* per-image Lovasz: images are independent sort problems, so each rank runs the
+  kernels on its slice of the batch and ONE all-reduce(sum) of a small fp64
+  buffer ``[sum of image losses, image count, per-class loss sums x C,
+  per-class presence counts x C]`` gives the global mean.  The backward needs no
+  collective: d(loss)/d(loss_b) = 1/B_global on the rank that owns image b.
+* confusion matrix: counts are additive, one all-reduce(sum) of n*n int64.
+* global-mode Lovasz does NOT shard (it needs one sort per class over all
+  pixels): under data parallelism every rank computes the loss of its local
+  batch, which is what DDP does with the reference ("replicas only").
+
+The functions below take tensors on whatever device the process group works on
+(CUDA/NCCL in production, CPU/gloo in the unit tests of the packing logic).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["pack_partials", "ShardedMeanOfImages", "sharded_per_image_mean", "lovasz_softmax_sharded",
+           "all_reduce_confusion", "shard_range"]
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced slice [lo, hi) of ``n_items`` for ``rank`` of ``world``."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_partials(group_loss: torch.Tensor, class_loss: torch.Tensor, class_present: torch.Tensor) -> torch.Tensor:
+    """fp64 buffer [sum_b loss_b, B_local, sum_b class_loss[b,:], sum_b present[b,:]]."""
+    c = class_loss.size(-1)
+    buf = torch.zeros(2 + 2 * c, dtype=torch.float64, device=group_loss.device)
+    buf[0] = group_loss.double().sum()
+    buf[1] = float(group_loss.numel())
+    buf[2:2 + c] = class_loss.double().view(-1, c).sum(0)
+    buf[2 + c:] = class_present.double().view(-1, c).sum(0)
+    return buf
+
+
+class ShardedMeanOfImages(torch.autograd.Function):
+    """mean over ALL ranks' images of the per-image losses; one all-reduce forward,
+    none backward."""
+
+    @staticmethod
+    def forward(ctx, local_sum, packed, group):
+        # packed[0] is the detached value of local_sum; the collective sums it over ranks
+        red = packed.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(red)
+        ctx.mark_non_differentiable(red)
+        return (red[0] / red[1]).to(local_sum.dtype), red
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_packed):
+        (packed,) = ctx.saved_tensors
+        return (grad_loss.double() / packed[1]).to(grad_loss.dtype), None, None
+
+
+def sharded_per_image_mean(group_loss, class_loss, class_present, group=None):
+    """Global per-image mean from this rank's per-image losses ``group_loss`` [B_local]
+    (differentiable w.r.t. ``group_loss``).  Returns (loss, stats) where stats holds the
+    reduced per-class loss means and presence counts for logging."""
+    packed = pack_partials(group_loss.detach(), class_loss.detach(), class_present.detach())
+    loss, packed = ShardedMeanOfImages.apply(group_loss.sum(), packed, group)
+    c = class_loss.size(-1)
+    counts = packed[2 + c:]
+    stats = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
+    return loss, stats
+
+
+def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None):
+    """per_image=True Lovasz-Softmax over a batch sharded across ranks: each rank
+    passes its own images; every rank gets the global loss; gradients stay local."""
+    from .lovasz_loss import lovasz_softmax
+
+    b_local = probas_local.size(0)
+    loss_local, outs = lovasz_softmax(probas_local, labels_local, per_image=True, ignore=ignore, return_outputs=True)
+    # loss_local is the mean over the local images; its sum over images carries the autograd graph
+    local_sum = loss_local * float(b_local)
+    packed = pack_partials(outs.group_loss, outs.class_loss, outs.class_present)
+    loss, packed = ShardedMeanOfImages.apply(local_sum, packed, group)
+    c = outs.class_loss.size(-1)
+    counts = packed[2 + c:]
+    stats = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
+    return loss, stats
+
+
+def all_reduce_confusion(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum an int64 [n,n] confusion matrix over the ranks in place (one collective)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist

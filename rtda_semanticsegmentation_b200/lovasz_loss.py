@@ -1,0 +1,269 @@
+"""Drop-in for the reference's ``losses/lovasz_loss.py`` on B200.
+
+Same names, arguments and error behaviour as the reference module
+(arman-rn/RTDA-SemanticSegmentation, losses/lovasz_loss.py):
+
+* ``LovaszSoftmax(reduction="mean", ignore=None)``  (:76-200) - ``forward(probas,
+  labels)``, ``prob_flatten`` (:93-120), ``lovasz_softmax_flat`` (:122-183);
+* free functions ``lovasz_grad`` (:47-70), ``mean`` (:19-44), ``isnan`` (:14-16);
+* the Berman spellings BASELINE.json names, which the reference file was adapted
+  from: ``lovasz_softmax``, ``lovasz_softmax_flat``, ``flatten_probas``.
+
+The loss and its gradient are computed by the hand-written sm_100a kernels in
+``csrc/lovasz.cu`` through the C ABI of ``include/rtda_lovasz.h``; PyTorch only
+owns the device memory, the stream and the autograd hook.  There is no CPU path:
+CPU tensors raise.
+
+Documented deviations from the reference:
+
+* an input with no valid pixel returns a 0-dim fp32 zero tensor with a zero
+  gradient where the reference returns the Python int 0 (which its own callers
+  crash on, train_lovasz.py:135);
+* ``per_image=True`` (absent from the reference) is
+  ``mean(forward(p[i:i+1], l[i:i+1]) for i in range(B))``;
+* inside a group of exactly equal errors the gradient follows a stable order
+  (ascending pixel index); the reference's order there is whatever the unstable
+  CPU sort produced;
+* labels outside ``[0, C)`` that are not ``ignore`` are treated as ignored unless
+  ``validate_labels=True``, which raises the reference's ``IndexError`` at the
+  cost of one host synchronisation.
+"""
+from __future__ import annotations
+
+from itertools import filterfalse
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = [
+    "LovaszSoftmax",
+    "lovasz_softmax",
+    "lovasz_softmax_flat",
+    "lovasz_grad",
+    "flatten_probas",
+    "mean",
+    "isnan",
+    "LovaszOutputs",
+]
+
+
+def isnan(x):
+    """True where ``x`` is NaN (lovasz_loss.py:14-16)."""
+    return x != x
+
+
+def mean(l, ignore_nan=False, empty=0):
+    """Generator-friendly mean with the reference's semantics (lovasz_loss.py:19-44):
+    sequential sum in iteration order, one value is returned as is, no value
+    returns ``empty`` (or raises ValueError when ``empty == "raise"``)."""
+    it = iter(l)
+    if ignore_nan:
+        it = filterfalse(isnan, it)
+    count = 0
+    total = None
+    for v in it:
+        total = v if count == 0 else total + v
+        count += 1
+    if count == 0:
+        if empty == "raise":
+            raise ValueError("Empty mean")
+        return empty
+    return total if count == 1 else total / count
+
+
+class LovaszOutputs:
+    """Side outputs of the last forward (device tensors, no synchronisation)."""
+
+    __slots__ = ("class_loss", "class_present", "n_present", "group_loss", "label_errors")
+
+    def __init__(self, class_loss, class_present, n_present, group_loss, label_errors):
+        self.class_loss = class_loss
+        self.class_present = class_present
+        self.n_present = n_present
+        self.group_loss = group_loss
+        self.label_errors = label_errors
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must be a CUDA tensor: rtda_semanticsegmentation_b200 has no CPU path "
+            "(the reference's CPU implementation is restated only in oracle/ for testing)")
+
+
+def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool):
+    """Runs rtda_lovasz_fwd.  probas [B,C,H,W] fp32 contiguous, labels [B,H,W] contiguous."""
+    lib = _lib.load()
+    b, c, h, w = probas.shape
+    hw = h * w
+    groups = b if per_image else 1
+    dev = probas.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nbytes = _lib.ctypes.c_size_t(0)
+        _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, int(per_image), _lib.ctypes.byref(nbytes)),
+                   "rtda_lovasz_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        unit = torch.empty(b * c * hw, dtype=torch.float32, device=dev) if need_grad else None
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        class_loss = torch.empty((groups, c), dtype=torch.float32, device=dev)
+        present = torch.empty((groups, c), dtype=torch.int32, device=dev)
+        n_present = torch.empty((groups,), dtype=torch.int32, device=dev)
+        group_loss = torch.empty((groups,), dtype=torch.float32, device=dev)
+        label_errors = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.rtda_lovasz_fwd(
+            probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
+            b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
+            ws.data_ptr(), nbytes.value,
+            unit.data_ptr() if unit is not None else None, loss.data_ptr(), class_loss.data_ptr(),
+            present.data_ptr(), n_present.data_ptr(), group_loss.data_ptr(), label_errors.data_ptr(),
+            stream), "rtda_lovasz_fwd")
+    return loss, unit, LovaszOutputs(class_loss, present, n_present, group_loss, label_errors), ws
+
+
+class _LovaszSoftmaxFunction(torch.autograd.Function):
+    """autograd hook around rtda_lovasz_fwd / rtda_lovasz_bwd."""
+
+    @staticmethod
+    def forward(ctx, probas, labels, ignore, per_image, holder):
+        need_grad = bool(ctx.needs_input_grad[0])
+        loss, unit, outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
+        if holder is not None:
+            holder.append(outs)
+        ctx.shape = tuple(probas.shape)
+        ctx.per_image = per_image
+        if need_grad:
+            ctx.save_for_backward(unit, outs.class_present, outs.n_present)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        unit, present, n_present = ctx.saved_tensors
+        b, c, h, w = ctx.shape
+        lib = _lib.load()
+        dev = unit.device
+        go = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous().view(1)
+        grad = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rtda_lovasz_bwd(
+                go.data_ptr(), unit.data_ptr(), present.data_ptr(), n_present.data_ptr(),
+                b, c, h * w, int(ctx.per_image), grad.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
+        return grad, None, None, None, None
+
+
+def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
+    if probas.dim() != 4:
+        raise ValueError(f"Expected 4D input, but got {probas.dim()}D")  # lovasz_loss.py:106-107
+    _require_cuda(probas, "probas")
+    _require_cuda(labels, "labels")
+    if probas.dtype == torch.float64:
+        raise TypeError("probas must be float32 / float16 / bfloat16 (the reference fails on float64 too)")
+    if probas.dtype != torch.float32:
+        probas = probas.float()  # the reference promotes through `fg.float() - probas_c` (:171)
+    probas = probas.contiguous()  # NCHW; a channels_last tensor is re-laid out once
+    labels.view(-1)  # same failure as lovasz_loss.py:118 for a non-contiguous target
+    if labels.dtype not in (torch.int64, torch.int32, torch.uint8):
+        labels = labels.long()
+    if labels.numel() != probas.size(0) * probas.size(2) * probas.size(3):
+        raise ValueError(f"labels {tuple(labels.shape)} do not match probas {tuple(probas.shape)}")
+    return probas, labels
+
+
+def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
+                   validate_labels=False, return_outputs=False):
+    """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
+    computes, lovasz_loss.py:185-200).
+
+    probas [B,C,H,W] class probabilities (softmax output), labels [B,H,W] int.
+    ``classes`` accepts 'present' and 'all'; the reference skips foreground-less
+    classes unconditionally (:167-168) so both average over present classes.
+    """
+    if classes not in ("present", "all"):
+        raise ValueError("classes must be 'present' or 'all'")
+    probas, labels = _as_kernel_inputs(probas, labels)
+    if probas.numel() == 0:
+        return probas.sum() * 0.0  # lovasz_loss.py:135-136
+    holder = []
+    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder)
+    outs = holder[0]
+    if validate_labels:
+        bad = int(outs.label_errors.item())
+        if bad:
+            raise IndexError(f"{bad} label value(s) outside [0, {probas.size(1)}) and not the ignore index")
+    return (loss, outs) if return_outputs else loss
+
+
+def flatten_probas(probas, labels, ignore=None):
+    """[B,C,H,W] -> [P,C], [B,H,W] -> [P], dropping ``ignore`` pixels (Berman's
+    helper; the reference's ``prob_flatten`` :93-120 is the ``ignore=None`` case)."""
+    if probas.dim() != 4:
+        raise ValueError(f"Expected 4D input, but got {probas.dim()}D")
+    c = probas.size(1)
+    flat = probas.permute(0, 2, 3, 1).contiguous().view(-1, c)
+    lab = labels.view(-1)
+    if ignore is None:
+        return flat, lab
+    keep = lab != ignore
+    return flat[keep], lab[keep]
+
+
+def lovasz_softmax_flat(probas, labels, classes="present", ignore=None):
+    """Flat form: probas [P,C], labels [P] (lovasz_loss.py:122-183).  The pixels are
+    re-laid out class-major once and run through the same kernels."""
+    if probas.dim() != 2:
+        raise ValueError(f"Expected 2D [P, C] input, but got {probas.dim()}D")
+    if probas.numel() == 0:
+        return probas * 0.0  # lovasz_loss.py:135-136
+    p4 = probas.t().contiguous().view(1, probas.size(1), probas.size(0), 1)
+    return lovasz_softmax(p4, labels.reshape(1, -1, 1), classes=classes, ignore=ignore)
+
+
+def lovasz_grad(gt_sorted):
+    """Gradient of the Lovasz extension w.r.t. sorted errors (lovasz_loss.py:47-70)
+    for a 1-D 0/1 tensor already in sorted order.  Device tensor in, device tensor
+    out.  The fused kernels never call this (they evaluate the same formula per
+    element from ranks); it is kept for API parity."""
+    _require_cuda(gt_sorted, "gt_sorted")
+    gt = gt_sorted.float()
+    p = gt.numel()
+    gts = gt.sum()
+    inter = gts - torch.cumsum(gt, 0)
+    union = gts + torch.cumsum(1.0 - gt, 0)
+    jac = 1.0 - inter / union
+    if p > 1:
+        jac[1:p] = jac[1:p] - jac[0:-1]
+    return jac
+
+
+class LovaszSoftmax(nn.Module):
+    """``LovaszSoftmax(ignore=255)(probas, labels)`` as in the reference
+    (lovasz_loss.py:76-200; constructed at main.py:299-302 and
+    main_adversarial.py:233-237).  Stateless; ``per_image`` and
+    ``validate_labels`` are additions (see the module docstring)."""
+
+    def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False):
+        super().__init__()
+        self.reduction = reduction
+        self.ignore = ignore
+        self.per_image = per_image
+        self.validate_labels = validate_labels
+        self.last_outputs = None
+
+    def prob_flatten(self, input, target):
+        """[B,C,H,W] -> [B*H*W, C] and [B,H,W] -> [B*H*W] (lovasz_loss.py:93-120)."""
+        return flatten_probas(input, target, ignore=None)
+
+    def lovasz_softmax_flat(self, probas, labels, classes="present"):
+        """Flat loss over [P,C] / [P] with this module's ignore index (:122-183)."""
+        return lovasz_softmax_flat(probas, labels, classes=classes, ignore=self.ignore)
+
+    def forward(self, probas, labels):
+        loss, outs = lovasz_softmax(probas, labels, classes="present", per_image=self.per_image,
+                                    ignore=self.ignore, validate_labels=self.validate_labels,
+                                    return_outputs=True) if probas.numel() else (lovasz_softmax(probas, labels), None)
+        self.last_outputs = outs
+        return loss

@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rtda_lovasz.h declares;
+argument validation that needs no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from rtda_semanticsegmentation_b200 import _lib
+
+
+def _declared_functions():
+    text = open(_lib.HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtda_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree():
+    assert _declared_functions() == sorted(_lib.SIGNATURES)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(raw, name), name
+
+
+def test_version_and_error_strings(lib):
+    assert lib.rtda_version() == 1
+    assert lib.rtda_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4):
+        assert lib.rtda_error_string(code).startswith(b"rtda:")
+
+
+def test_workspace_query_and_argument_errors(lib):
+    n = ctypes.c_size_t(0)
+    assert lib.rtda_lovasz_workspace_bytes(4, 19, 512 * 1024, 0, ctypes.byref(n)) == 0
+    pairs = 2 * 19 * 4 * 512 * 1024 * 8  # the two (key, payload) ping-pong buffers dominate
+    assert pairs < n.value < pairs * 1.2
+    n2 = ctypes.c_size_t(0)
+    assert lib.rtda_lovasz_workspace_bytes(4, 19, 512 * 1024, 1, ctypes.byref(n2)) == 0
+    assert abs(n2.value - n.value) < 0.05 * n.value
+    assert lib.rtda_lovasz_workspace_bytes(0, 19, 10, 0, ctypes.byref(n)) == -1       # RTDA_E_ARG
+    assert lib.rtda_lovasz_workspace_bytes(1, 45, 10, 0, ctypes.byref(n)) == -2       # > RTDA_MAX_CLASSES
+    assert lib.rtda_lovasz_workspace_bytes(1, 19, 1 << 30, 0, ctypes.byref(n)) == -2  # segment too long
+    assert lib.rtda_lovasz_workspace_bytes(1, 19, 10, 0, None) == -1
+    # null pointers are rejected before anything is launched
+    assert lib.rtda_lovasz_fwd(None, None, 0, 1, 19, 16, 255, 1, 0, None, 0, None, None, None, None, None, None, None, None) == -1
+    assert lib.rtda_lovasz_bwd(None, None, None, None, 1, 19, 16, 0, None, None) == -1
+    assert lib.rtda_confusion_accumulate(None, 0, None, 0, 10, 19, 255, 1, None, None) == -1
+    assert lib.rtda_confusion_argmax_accumulate(None, None, 0, 1, 19, 16, 255, 1, None, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.NativeLibraryError):
+        _lib.load()

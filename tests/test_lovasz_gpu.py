@@ -1,0 +1,213 @@
+"""GPU: parity of the CUDA Lovasz-Softmax path (through the C ABI) with the oracle and
+with the golden vectors written from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): loss and gradient within 1e-5 relative of the
+reference; here the loss is held to 2e-6 relative and the gradient is compared BIT FOR BIT
+with the stable-order C oracle (which itself equals the reference wherever errors are
+distinct, tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_case
+from oracle import c_oracle
+import rtda_semanticsegmentation_b200 as rtda
+from rtda_semanticsegmentation_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 2e-6
+
+
+def run_cuda(probas, labels, ignore=255, per_image=False, grad_out=None, label_dtype=None, module=True):
+    p = torch.as_tensor(probas).cuda().requires_grad_(True)
+    l = torch.as_tensor(labels).cuda()
+    if label_dtype is not None:
+        l = l.to(label_dtype)
+    if module:
+        crit = rtda.LovaszSoftmax(ignore=ignore, per_image=per_image)
+        loss = crit(p, l)
+    else:
+        loss = rtda.lovasz_softmax(p, l, per_image=per_image, ignore=ignore)
+    assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.is_cuda
+    (loss if grad_out is None else loss * grad_out).backward()
+    torch.cuda.synchronize()
+    return float(loss.item()), p.grad.cpu().numpy()
+
+
+def assert_matches_oracle(probas, labels, ignore=255, per_image=False, grad_out=None, tag="", **kw):
+    probas = np.asarray(probas, np.float32)
+    labels = np.asarray(labels, np.int64)
+    want = c_oracle.lovasz(probas, labels, ignore, per_image, grad_out=1.0 if grad_out is None else grad_out)
+    loss, grad = run_cuda(probas, labels, ignore, per_image, grad_out, **kw)
+    assert abs(loss - float(want["loss"])) <= LOSS_RTOL * max(abs(float(want["loss"])), 1e-30), (tag, loss, want["loss"])
+    if not np.array_equal(grad, want["grad"]):
+        bad = np.argwhere(grad != want["grad"])
+        raise AssertionError(f"{tag}: {len(bad)} of {grad.size} gradient elements differ; first {bad[:5].tolist()} "
+                             f"got {grad[tuple(bad[0])]} want {want['grad'][tuple(bad[0])]}; "
+                             f"max abs diff {np.abs(grad - want['grad']).max():.3e} of max {np.abs(want['grad']).max():.3e}")
+    return loss, grad
+
+
+def test_golden_vectors(lovasz_golden):
+    for name in [str(n) for n in lovasz_golden["names"]]:
+        c = golden_case(lovasz_golden, name)
+        loss, grad = assert_matches_oracle(c["probas"], c["labels"], c["ignore"], c["per_image"], tag=name)
+        # against what the unmodified reference returned
+        assert abs(loss - c["loss"]) <= 1e-5 * max(abs(c["loss"]), 1e-30), name
+        if not c["ties"]:
+            gmax = np.abs(c["grad"]).max()
+            assert np.abs(grad - c["grad"]).max() <= 1e-5 * gmax, name
+            assert np.array_equal(grad, c["grad"]), name        # in fact bit for bit
+
+
+def test_kat1_by_hand():
+    # loss 0.5666666627, grads known in closed form
+    ch1 = torch.tensor([0.9, 0.6, 0.3, 0.2])
+    p = torch.stack([1 - ch1, ch1]).view(1, 2, 1, 4)
+    loss, grad = run_cuda(p, torch.tensor([[[1, 0, 1, 255]]]))
+    assert loss == pytest.approx(0.5666666626930237, abs=1e-7)
+    np.testing.assert_allclose(grad[0, 0, 0], [0, -0.25, 0.25, 0], atol=1e-7)
+    np.testing.assert_allclose(grad[0, 1, 0], [-0.166666687, 0.083333313, -0.25, 0], atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(1, 19, 16, 24), (2, 19, 37, 53), (3, 5, 7, 13), (1, 2, 1, 1), (2, 3, 1, 5),
+                                   (1, 19, 64, 65), (5, 7, 33, 31), (1, 44, 20, 20), (2, 19, 128, 256)])
+@pytest.mark.parametrize("per_image", [False, True])
+def test_random_shapes(shape, per_image):
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(b * 1000 + c * 100 + h + w)
+    probas = torch.softmax(torch.randn((b, c, h, w), generator=g) * 2.5, 1)
+    labels = torch.randint(0, c, (b, h, w), generator=g)
+    labels[torch.rand((b, h, w), generator=g) < 0.12] = 255
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, per_image, tag=f"{shape} per_image={per_image}")
+
+
+def test_ignore_none_and_out_of_range_labels():
+    g = torch.Generator().manual_seed(5)
+    probas = torch.softmax(torch.randn((2, 6, 9, 11), generator=g), 1)
+    labels = torch.randint(0, 6, (2, 9, 11), generator=g)
+    assert_matches_oracle(probas.numpy(), labels.numpy(), None, False, tag="ignore=None")
+    labels[0, 0, :3] = 77          # out of range, not the ignore index: treated as ignored, and counted
+    labels[1, 2, 2] = -4
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="out of range")
+    crit = rtda.LovaszSoftmax(ignore=255)
+    crit(probas.cuda(), labels.cuda())
+    assert int(crit.last_outputs.label_errors.item()) == 4
+    with pytest.raises(IndexError):
+        rtda.LovaszSoftmax(ignore=255, validate_labels=True)(probas.cuda(), labels.cuda())
+
+
+def test_all_ignored_returns_zero_tensor_with_zero_grad():
+    p = torch.rand(2, 5, 4, 4).softmax(1)
+    l = torch.full((2, 4, 4), 255)
+    for per_image in (False, True):
+        loss, grad = run_cuda(p, l, 255, per_image)
+        assert loss == 0.0 and not grad.any()
+
+
+def test_heavy_ties_follow_the_documented_stable_order():
+    g = torch.Generator().manual_seed(9)
+    labels = torch.randint(0, 5, (2, 40, 40), generator=g)
+    labels[torch.rand((2, 40, 40), generator=g) < 0.1] = 255
+    uniform = torch.full((2, 5, 40, 40), 0.2)
+    assert_matches_oracle(uniform.numpy(), labels.numpy(), tag="uniform")
+    onehot = torch.zeros(2, 5, 40, 40).scatter_(1, torch.randint(0, 5, (2, 1, 40, 40), generator=g), 1.0)
+    assert_matches_oracle(onehot.numpy(), labels.numpy(), tag="one-hot (errors exactly 0 and 1)")
+    quant = torch.randint(0, 5, (2, 5, 40, 40), generator=g).float() / 4
+    assert_matches_oracle(quant.numpy(), labels.numpy(), tag="quantised")
+
+
+def test_out_of_domain_probabilities():
+    # the kernels sort all 32 key bits and carry sgn(fg - p): values outside [0,1] behave like the reference
+    g = torch.Generator().manual_seed(10)
+    probas = torch.randn((1, 4, 12, 12), generator=g) * 2
+    labels = torch.randint(0, 4, (1, 12, 12), generator=g)
+    assert_matches_oracle(probas.numpy(), labels.numpy(), tag="out of domain")
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int32])
+def test_label_dtypes(dtype):
+    probas, labels = synthetic.confident_case(2, 48, 64, seed=21)
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag=str(dtype), label_dtype=dtype)
+
+
+def test_grad_out_scales_exactly_like_autograd():
+    probas, labels = synthetic.diffuse_case(2, 32, 48, seed=22)
+    for per_image in (False, True):
+        assert_matches_oracle(probas.numpy(), labels.numpy(), 255, per_image, grad_out=32768.0 * 0.5, tag="scaled")
+
+
+def test_half_precision_inputs_and_autocast():
+    probas, labels = synthetic.confident_case(1, 32, 32, seed=23)
+    want = c_oracle.lovasz(probas.half().float().numpy(), labels.numpy(), 255, False)
+    p16 = probas.half().cuda().requires_grad_(True)
+    loss = rtda.LovaszSoftmax(ignore=255)(p16, labels.cuda())
+    loss.backward()
+    assert loss.dtype == torch.float32                                   # the reference promotes to fp32
+    assert float(loss) == pytest.approx(float(want["loss"]), rel=LOSS_RTOL)
+    assert p16.grad.dtype == torch.float16
+    logits = torch.randn(1, 19, 32, 32, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        pr = torch.softmax(logits, 1)                                    # fp32 under autocast (train_lovasz.py:101)
+        lv = rtda.LovaszSoftmax(ignore=255)(pr, labels.cuda())
+    lv.backward()
+    assert lv.dtype == torch.float32 and torch.isfinite(logits.grad).all()
+
+
+def test_channels_last_and_flat_api():
+    probas, labels = synthetic.confident_case(2, 24, 40, seed=24)
+    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, False)
+    pcl = probas.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    loss = rtda.LovaszSoftmax(ignore=255)(pcl, labels.cuda())
+    loss.backward()
+    assert float(loss) == pytest.approx(float(want["loss"]), rel=LOSS_RTOL)
+    assert np.array_equal(pcl.grad.cpu().numpy(), want["grad"])
+    crit = rtda.LovaszSoftmax(ignore=255)
+    flat_p, flat_l = crit.prob_flatten(probas.cuda().requires_grad_(True), labels.cuda())
+    lf = crit.lovasz_softmax_flat(flat_p, flat_l)                        # lovasz_loss.py:122-183 signature
+    assert float(lf) == pytest.approx(float(want["loss"]), rel=LOSS_RTOL)
+    lb = rtda.lovasz_softmax(probas.cuda(), labels.cuda(), classes="all", ignore=255)
+    assert float(lb) == float(loss)
+
+
+def test_loss_only_under_no_grad_and_repeatability():
+    probas, labels = synthetic.confident_case(2, 64, 64, seed=25)
+    p, l = probas.cuda(), labels.cuda()
+    with torch.no_grad():
+        a = rtda.LovaszSoftmax(ignore=255)(p, l)
+    outs = []
+    for _ in range(3):
+        q = p.clone().requires_grad_(True)
+        v = rtda.LovaszSoftmax(ignore=255)(q, l)
+        v.backward()
+        outs.append((float(v), q.grad.clone()))
+    assert float(a) == outs[0][0]
+    assert all(o[0] == outs[0][0] and torch.equal(o[1], outs[0][1]) for o in outs)   # deterministic, run to run
+
+
+def test_lovasz_grad_free_function():
+    gt = torch.tensor([1, 0, 1, 0, 0], dtype=torch.float32, device="cuda")
+    np.testing.assert_allclose(rtda.lovasz_grad(gt).cpu().numpy(), [0.5, 0.166666627, 0.333333373, 0, 0], atol=1e-8)
+    assert rtda.lovasz_grad(torch.ones(1, device="cuda")).item() == 1.0
+
+
+@pytest.mark.parametrize("cfg", ["c1_global", "c2_global", "c2_per_image"])
+def test_baseline_configs_full_size_bit_exact(cfg):
+    """BASELINE.json configs[0] and configs[1] at full size against the C oracle (seconds on CPU)."""
+    b = 1 if cfg == "c1_global" else 4
+    probas, labels = synthetic.confident_case(b, 512, 1024, seed=1234 + 100 * (1 if b == 1 else 2), device="cuda")
+    per_image = cfg.endswith("per_image")
+    loss, grad = assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, per_image, tag=cfg)
+    # size-independent invariants
+    lab = labels.cpu().numpy()
+    ign = lab == 255
+    assert not grad.transpose(0, 2, 3, 1)[ign].any()                     # (i) zero at ignored pixels
+    total = np.abs(grad.astype(np.float64)).sum()
+    assert total == pytest.approx(1.0, abs=1e-4)                          # (iii) sum |dL/dp| = 1
+    assert 0.0 < loss < 1.0
+
+
+def test_diffuse_distribution_full_size():
+    probas, labels = synthetic.diffuse_case(1, 512, 1024, seed=1334, device="cuda")
+    assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, False, tag="diffuse c1")
