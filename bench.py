@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the Lovasz-Softmax fwd+bwd hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
+
+One "step" = one forward + backward of the loss over one batch of synthetic input
+(`LovaszSoftmax(ignore=255)(probas, labels)`; `loss.backward()`).  Prints ONE JSON line.
+
+* N = 1 (default): workload c2 = BASELINE.json configs[1], 4x19x512x1024, global
+  (per_image=False), classes='present', D_conf synthetic distribution.
+* N > 1 (torchrun, one rank per GPU): the path shards per image, so every rank runs
+  per_image=True on its own 4x19x512x1024 slice of a 4N-image batch and ONE NCCL
+  all-reduce of the 40-double partial buffer gives the global loss (weak scaling).
+* `value`   - Mpix/s (pixels = B*H*W incl. ignored) with inputs resident in HBM; several
+  input sets larger than L2 are rotated so no step finds its inputs in L2.
+* `e2e`     - the same through the public API from pinned HOST buffers: H2D of probas and
+  labels and D2H of the loss inside the timed region.
+* `roofline` - algorithmic bytes (160 B/px) / step time against the measured
+  HBM peak of MEASURED_PEAKS.json; `kernels` lists every kernel's live CUDA-event time.
+* `cpu_baseline` - the oracle port of the reference's CPU path timed on this box's cores.
+* `--impl reference` - the reference arm: the same oracle port (the reference is Python
+  and does not travel to the GPU box; oracle/lovasz_oracle.py restates it op for op).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PX = 160.0   # read 19 fp32 probs + 1 int64 label, write 19 fp32 grads
+CM_BYTES_PER_PX = 16.0      # int64 label + int64 prediction
+
+WORKLOADS = {
+    # name: (images per GPU, H, W, per_image at N=1, description)
+    "c1": (1, 512, 1024, False, "configs[0]: 1x19x512x1024 global"),
+    "c2": (4, 512, 1024, False, "configs[1]: 4x19x512x1024 global, classes=present"),
+    "c3": (16, 720, 1280, True, "configs[2]: 16x19x720x1280 per_image (Lovasz only), batch sharded over ranks"),
+    "c5": (8, 512, 1024, False, "configs[4]: 8x19x512x1024 global"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons polled through NVML (nvidia_ml_py) every ~2 ms DURING the
+    timed region; falls back to one nvidia-smi query when NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.index = index
+        self.sm = []
+        self.bits = 0
+        self.max_mhz = None
+        self.power = []
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _loop(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception as e:  # keep sampling what we can
+                self.err = repr(e)
+            time.sleep(0.002)
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.err = repr(e)
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(x) for x in out.strip().split(",")[:2]]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "note": f"nvml unavailable ({self.err}); one nvidia-smi sample after the region"}
+            except Exception as e:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {self.err} / {e!r}"], "samples": 0}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
+
+
+def reference_port_step(probas_cpu, labels_cpu, per_image):
+    """One fwd+bwd of the reference's CPU path as restated op for op in oracle/lovasz_oracle.py
+    (unstable torch.sort exactly like lovasz_loss.py:173)."""
+    from oracle import lovasz_oracle
+
+    lovasz_oracle.lovasz_softmax_with_grad(probas_cpu, labels_cpu, ignore=255, per_image=per_image, stable=False)
+
+
+def time_reference_port(probas_cpu, labels_cpu, per_image, budget_s, steps, warmup):
+    """Times the oracle port on a bounded sample: as many leading images as fit the budget."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = probas_cpu.size(0)
+    t0 = time.perf_counter()
+    reference_port_step(probas_cpu[:1], labels_cpu[:1], per_image)
+    t1 = time.perf_counter() - t0
+    imgs = max(1, min(b, int(budget_s / max(t1, 1e-3) / max(steps + warmup, 1))))
+    p, l = probas_cpu[:imgs].contiguous(), labels_cpu[:imgs].contiguous()
+    for _ in range(warmup):
+        reference_port_step(p, l, per_image)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        reference_port_step(p, l, per_image)
+        times.append(time.perf_counter() - t0)
+    px = imgs * p.size(2) * p.size(3)
+    return px, times, imgs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--distribution", default="conf", choices=["conf", "diffuse"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    imgs, H, W, per_image_n1, desc = WORKLOADS[args.workload]
+    C = 19
+    from rtda_semanticsegmentation_b200 import synthetic
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        gen = synthetic.confident_case if args.distribution == "conf" else synthetic.diffuse_case
+        cfg_id = {"c1": 1, "c2": 2, "c3": 3, "c5": 5}[args.workload]
+        probas, labels = gen(min(imgs, 4), H, W, seed=1234 + 100 * cfg_id)
+        per_image = per_image_n1 or world > 1
+        px, times, used = time_reference_port(probas, labels, per_image, 150.0, args.steps, args.warmup)
+        t = sum(times) / len(times)
+        val = px / t / 1e6
+        line = {
+            "impl": "reference", "metric": "lovasz_softmax_fwd_bwd_mpix_per_s", "value": val, "unit": "Mpix/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "classes": C, "distribution": "D_" + args.distribution,
+                       "per_image": per_image},
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"first {used} image(s) of the workload per step ({used}x{C}x{H}x{W}), "
+                                       "oracle/lovasz_oracle.py torch-CPU restatement of losses/lovasz_loss.py"},
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import rtda_semanticsegmentation_b200 as rtda
+    from rtda_semanticsegmentation_b200 import _lib
+    from rtda_semanticsegmentation_b200.dist import lovasz_softmax_sharded
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    per_image = per_image_n1 or world > 1
+    if args.workload == "c3":
+        imgs = max(1, imgs // world)       # configs[2]: strong split of the 16-image batch
+        scaling = "strong"
+    else:
+        scaling = "weak"
+    cfg_id = {"c1": 1, "c2": 2, "c3": 3, "c5": 5}[args.workload]
+    gen = synthetic.confident_case if args.distribution == "conf" else synthetic.diffuse_case
+
+    # several distinct input sets, together larger than L2 (126 MB), rotated every step
+    set_bytes = imgs * H * W * (4 * C + 8)
+    n_sets = max(2, min(6, -(-400 * 1024 * 1024 // set_bytes)))
+    sets = []
+    for i in range(n_sets):
+        p, l = gen(imgs, H, W, seed=1234 + 100 * cfg_id + rank + 1000 * i, device=dev)
+        sets.append((p.contiguous(), l.contiguous()))
+    px_step = imgs * H * W
+    crit = rtda.LovaszSoftmax(ignore=255, per_image=per_image)
+
+    def step(p, l):
+        p = p.detach().requires_grad_(True)
+        if world > 1:
+            loss, _ = lovasz_softmax_sharded(p, l, ignore=255)
+        else:
+            loss = crit(p, l)
+        loss.backward()
+        return loss, p.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(*sets[i % n_sets])
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, per-kernel events on
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    host_t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss, grad = step(*sets[i % n_sets])
+    host_ms_step = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host enqueue time, no sync inside
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+    loss_value = float(loss.item())
+
+    # ---- timed region 2: end to end from pinned host buffers.  Every step's probas + labels are
+    # copied host -> device inside the region (double-buffered on a side stream so the copy of step
+    # i+1 overlaps the kernels of step i) and every step's loss is copied back to the host.
+    from rtda_semanticsegmentation_b200.host_pipeline import DeviceStager
+
+    hp = [(p.cpu().pin_memory(), l.cpu().pin_memory()) for p, l in sets[:2]]
+    stager = DeviceStager(sets[0], dev, depth=2)
+    host_loss = torch.empty((args.steps + 8,), dtype=torch.float32).pin_memory()
+
+    def e2e_run(n):
+        slot = stager.submit(hp[0])
+        for i in range(n):
+            nxt = stager.submit(hp[(i + 1) % 2]) if i + 1 < n else None
+            dp, dl = stager.acquire(slot)
+            loss, _ = step(dp, dl)
+            stager.release(slot)
+            host_loss[i].copy_(loss.detach(), non_blocking=True)
+            slot = nxt
+
+    e2e_run(3)
+    barrier()
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item()) / args.steps
+    e2e_value = world * px_step / (e2e_ms * 1e-3) / 1e6
+    assert abs(float(host_loss[args.steps - 1]) - float(step(*sets[(args.steps - 1) % 2])[0])) < 1e-6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    algo_bytes = ALGO_BYTES_PER_PX * px_step
+    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    # per-kernel compulsory traffic of each stage's own job (bytes per launch), for the kernel table
+    E = C * px_step
+    own_bytes = {
+        "memset_workspace": None,
+        "k_hist": px_step * (4 * C + 8 + 1),
+        "k_scan": None,
+        "k_sort_pass<0,probas>": E * 4 + px_step * 1 + E * 8,
+        "k_sort_pass<1>": E * 16,
+        "k_sort_pass<2>": E * 16,
+        "k_rank_last": E * 8 + E * 4,
+        "k_finalize": None,
+        "k_bwd": E * 8,
+    }
+    kernels = []
+    launches = 0
+    for name, (ms, cnt) in stages.items():
+        if name == "gaps_between_launches":
+            continue
+        if name != "memset_workspace":
+            launches += cnt
+        per = ms / max(cnt, 1)
+        ob = own_bytes.get(name)
+        kernels.append({"name": name, "launches": int(cnt), "ms_per_launch": round(per, 5),
+                        "share_of_step": round(ms / args.steps / ms_step, 4),
+                        "own_gbs": round(ob / (per * 1e-3) / 1e9, 1) if ob and per > 0 else None,
+                        "own_frac_of_peak": round(ob / (per * 1e-3) / 1e9 / peak, 4) if ob and per > 0 else None})
+    kernels.sort(key=lambda k: -k["share_of_step"])
+    dom = kernels[0]
+    gaps = stages.get("gaps_between_launches", (0.0, 0))
+
+    line = {
+        "metric": "lovasz_softmax_fwd_bwd_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "host_enqueue_ms_per_step": host_ms_step,
+        "gap_ms_per_step": gaps[0] / args.steps, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {desc}" + ("" if world == 1 else f"; per rank {imgs}x{C}x{H}x{W}, per_image=True sharded over {world} ranks, 1 all-reduce of 40 doubles"),
+            "classes": C, "ignore": 255, "per_image": per_image, "distribution": "D_" + args.distribution,
+            "labels": "int64", "l2_policy": f"{n_sets} distinct input sets ({n_sets * set_bytes >> 20} MiB > 126 MiB L2) rotated every step",
+            "loss": loss_value,
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(set_bytes), "d2h_bytes_per_step": 4,
+                "note": "per step: pinned host probas+labels -> H2D (side stream, overlapping the previous step's kernels) -> LovaszSoftmax fwd+bwd -> loss D2H; the gradient stays on the device as in training"},
+        "gpu_launches": int(launches),
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "what": "whole fwd+bwd step: 160 B/px algorithmic bytes x pixels / CUDA-event step time (the sort passes move ~1.2 KB/px, so the algorithmic fraction is far below each kernel's own DRAM fraction)",
+            "dominant_kernel": dom["name"], "dominant_share_of_step": dom["share_of_step"],
+            "dominant_own_gbs": dom["own_gbs"], "dominant_own_frac_of_peak": dom["own_frac_of_peak"],
+            "kernels": kernels,
+        },
+    }
+
+    if not args.no_cpu_baseline and world == 1:
+        p_cpu, l_cpu = sets[0][0].cpu(), sets[0][1].cpu()
+        px, times, used = time_reference_port(p_cpu, l_cpu, per_image, args.cpu_budget_s, 2, 1)
+        tb = min(times)
+        line["cpu_baseline"] = {
+            "value": px / tb / 1e6, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {used} image(s) of the workload ({used}x{C}x{H}x{W}), 1 warm-up + 2 timed, best; "
+                      "oracle/lovasz_oracle.py torch-CPU restatement of losses/lovasz_loss.py",
+        }
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

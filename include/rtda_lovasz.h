@@ -114,6 +114,18 @@ int rtda_confusion_argmax_accumulate(const float *logits, const void *labels, in
                                      int64_t B, int n_class, int64_t HW, int64_t ignore, int has_ignore,
                                      int64_t *hist, void *stream);
 
+/* ---- Per-kernel timing (benchmark aid) ---------------------------------------
+ * When enabled, every kernel launch of this library is bracketed by two CUDA
+ * events recorded on the launch stream.  rtda_profile_read synchronises the
+ * device, ADDS the elapsed milliseconds and launch counts per stage since the
+ * last read into the caller's host arrays, and recycles the events.  Off by
+ * default; meant for single-threaded benchmark use (the event list is global).
+ * Stages: see rtda_profile_stage_name(0 .. RTDA_PROFILE_STAGES-1). */
+#define RTDA_PROFILE_STAGES 12
+int rtda_profile_enable(int on);
+int rtda_profile_read(double *stage_ms_host, int64_t *stage_launches_host, int n_stages);
+const char *rtda_profile_stage_name(int stage);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "librtda_lovasz_b200.so")
+# RTDA_LIB_PATH selects another build of the same library (kernel-variant experiments only)
+LIB_PATH = os.environ.get("RTDA_LIB_PATH") or os.path.join(_PKG, "librtda_lovasz_b200.so")
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "rtda_lovasz.h")
 
 LABEL_I64, LABEL_U8, LABEL_I32 = 0, 1, 2
@@ -30,7 +31,25 @@ SIGNATURES = {
     "rtda_lovasz_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "rtda_confusion_accumulate": (_int, [_vp, _int, _vp, _int, _i64, _int, _i64, _int, _vp, _vp]),
     "rtda_confusion_argmax_accumulate": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _vp, _vp]),
+    "rtda_profile_enable": (_int, [_int]),
+    "rtda_profile_read": (_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), _int]),
+    "rtda_profile_stage_name": (ctypes.c_char_p, [_int]),
 }
+
+PROFILE_STAGES = 12
+
+
+def profile_enable(on: bool) -> None:
+    check(load().rtda_profile_enable(int(on)), "rtda_profile_enable")
+
+
+def profile_read():
+    """{stage name: (total ms, launches)} since the last read (synchronises the device)."""
+    ms = (ctypes.c_double * PROFILE_STAGES)()
+    cnt = (ctypes.c_int64 * PROFILE_STAGES)()
+    check(load().rtda_profile_read(ms, cnt, PROFILE_STAGES), "rtda_profile_read")
+    lib = load()
+    return {lib.rtda_profile_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(PROFILE_STAGES) if cnt[i]}
 
 _lib = None
 

@@ -21,6 +21,21 @@ typedef unsigned long long u64;
 
 namespace rtda {
 
+// Optional per-launch timing (profile.cu).  A ProfileScope brackets one launch with two
+// events on the launch stream when profiling is enabled; otherwise it does nothing.
+enum Stage {
+    kStageMemset = 0, kStageHist, kStageScan, kStagePass0, kStagePass1, kStagePass2, kStageRankLast,
+    kStageFinalize, kStageBwd, kStageConfusion, kStageConfusionArgmax, kStageOther
+};
+bool profile_enabled();
+void profile_begin(int stage, cudaStream_t st);
+void profile_end(int stage, cudaStream_t st);
+struct ProfileScope {
+    int stage; cudaStream_t st; bool on;
+    ProfileScope(int s, cudaStream_t t) : stage(s), st(t), on(profile_enabled()) { if (on) profile_begin(stage, st); }
+    ~ProfileScope() { if (on) profile_end(stage, st); }
+};
+
 __device__ __forceinline__ u32 lanemask_lt() {
     u32 m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

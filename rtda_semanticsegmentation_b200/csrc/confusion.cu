@@ -141,6 +141,7 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
     auto *h = reinterpret_cast<unsigned long long *>(hist);
     const LabelT *l = (const LabelT *)labels;
     const PredT *p = (const PredT *)preds;
+    ProfileScope ps(kStageConfusion, st);
     if (mode == 0) {
         if (smem > 48 * 1024)
             RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion<LabelT, PredT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -179,6 +180,7 @@ static int launch_confusion_argmax(const float *logits, const void *labels, long
     if (grid < 1) grid = 1;
     auto *h = reinterpret_cast<unsigned long long *>(hist);
     const LabelT *l = (const LabelT *)labels;
+    ProfileScope ps(kStageConfusionArgmax, st);
     if (mode == 0) {
         if (smem > 48 * 1024)
             RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion_argmax<LabelT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

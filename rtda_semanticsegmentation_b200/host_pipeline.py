@@ -1,0 +1,48 @@
+"""Double-buffered pinned-host -> device staging for callers whose batches live on the host.
+
+The reference moves every batch with a blocking ``.to(device)`` (train_lovasz.py:65-66,
+validation.py:83-84).  On B200 the loss kernels take ~1.4 ms for a 4x19x512x1024 batch while
+the 176 MB host->device copy of its inputs takes ~3 ms over PCIe, so the copy of batch i+1
+has to overlap the kernels of batch i: copies run on a side stream into ``depth`` rotating
+device slots, CUDA events order them against the compute stream.  No host synchronisation.
+"""
+from __future__ import annotations
+
+import torch
+
+__all__ = ["DeviceStager"]
+
+
+class DeviceStager:
+    """``submit(host_tensors)`` starts the async copies of one batch and returns a slot id;
+    ``acquire(slot)`` makes the current stream wait for them and returns the device tensors;
+    ``release(slot)`` marks the point after which the slot may be overwritten."""
+
+    def __init__(self, like, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in like] for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth
+        self.next = 0
+
+    def submit(self, host_tensors):
+        slot = self.next
+        self.next = (self.next + 1) % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[slot] is not None:
+                self.copy_stream.wait_event(self.free[slot])   # kernels that read this slot have finished
+            for dst, src in zip(self.slots[slot], host_tensors):
+                dst.copy_(src, non_blocking=True)              # src must be pinned for a truly async copy
+            self.ready[slot].record(self.copy_stream)
+        return slot
+
+    def acquire(self, slot):
+        torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        return self.slots[slot]
+
+    def release(self, slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev
