@@ -47,6 +47,8 @@ WORKLOADS = {
     "c2": (4, 512, 1024, False, "configs[1]: 4x19x512x1024 global, classes=present"),
     "c3": (16, 720, 1280, True, "configs[2]: 16x19x720x1280 per_image (Lovasz only), batch sharded over ranks"),
     "c5": (8, 512, 1024, False, "configs[4]: 8x19x512x1024 global"),
+    # configs[3] is the confusion-matrix path (its own metric): see bench_confusion()
+    "c4": (1, 1024, 2048, False, "configs[3]: validation confusion matrix, 1024x2048 int64 label + prediction maps, images sharded over ranks"),
 }
 
 
@@ -142,6 +144,112 @@ def time_reference_port(probas_cpu, labels_cpu, per_image, budget_s, steps, warm
     return px, times, imgs
 
 
+def bench_confusion(args, rank, local_rank, world):
+    """configs[3]: one step = one 1024x2048 validation map pair accumulated into the 19x19 matrix
+    (validation.py:98-109).  Maps are sharded over ranks; ONE all-reduce of the counts at the end,
+    inside the timed region.  16 algorithmic bytes per pixel."""
+    import numpy as np
+
+    import rtda_semanticsegmentation_b200 as rtda
+    from rtda_semanticsegmentation_b200 import _lib, synthetic
+
+    _, H, W, _, desc = WORKLOADS["c4"]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_sets = 10                                             # 10 x 33.5 MB = 335 MB > L2
+    maps = [synthetic.validation_maps(1, H, W, seed=1234 + 400 + rank + 100 * i, device=dev) for i in range(n_sets)]
+    px = H * W
+    cm = rtda.ConfusionMatrix(19, 255, device=dev)
+    warmup = max(args.warmup, 3)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        cm.update(*maps[i % n_sets])
+    cm.reset()
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        cm.update(*maps[i % n_sets])
+    cm.all_reduce()
+    e1.record()
+    sync()
+    clocks = sampler.stop() if rank == 0 else None
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * px / (ms_step * 1e-3) / 1e6
+    total = int(cm.compute().sum())
+
+    # end to end through the reference signature: numpy maps on the host -> fast_hist -> numpy matrix
+    host = [(l.cpu().numpy().ravel(), p.cpu().numpy().ravel()) for l, p in maps[:3]]
+    for i in range(3):
+        rtda.fast_hist(*host[i % 3], 19)
+    sync()
+    t0 = time.perf_counter()
+    acc = np.zeros((19, 19))
+    for i in range(args.steps):
+        acc += rtda.fast_hist(*host[i % 3], 19)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    k_ms, k_n = stages.get("k_confusion", (0.0, 1))
+    per = k_ms / max(k_n, 1)
+    achieved = CM_BYTES_PER_PX * px / (per * 1e-3) / 1e9
+    line = {
+        "metric": "confusion_matrix_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"c4: {desc}", "classes": 19, "ignore": 255, "maps_per_step": 1,
+                   "l2_policy": f"{n_sets} distinct map pairs ({n_sets * px * 16 >> 20} MiB > 126 MiB L2) rotated every step",
+                   "counted_pixels": total},
+        "clocks": clocks,
+        "e2e": {"value": world * px / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": px * 16, "d2h_bytes_per_step": 19 * 19 * 8,
+                "note": "rtda.fast_hist(label_true_np, label_pred_np, 19): pageable numpy maps -> H2D -> kernel -> 19x19 int64 D2H, wall clock"},
+        "gpu_launches": int(k_n),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "dominant_kernel": "k_confusion",
+                     "ms_per_launch": per, "what": "16 B/px (int64 label + int64 prediction) x 2097152 px / k_confusion CUDA-event time"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import hist_oracle
+        l, p = maps[0][0].cpu().numpy(), maps[0][1].cpu().numpy()
+        hist_oracle.validation_confusion(l, p, 19, 255)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            hist_oracle.validation_confusion(l, p, 19, 255)
+            ts.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": px / min(ts) / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                "sample": "one 1024x2048 map, best of 5; oracle/hist_oracle.py numpy restatement of "
+                                          "validation.py:98-109 + utils.py:62-89 (np.bincount is single-threaded)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +266,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "c4" and args.impl == "ours":
+        return bench_confusion(args, rank, local_rank, world)
     imgs, H, W, per_image_n1, desc = WORKLOADS[args.workload]
     C = 19
     from rtda_semanticsegmentation_b200 import synthetic
@@ -167,6 +277,27 @@ def main():
         if rank != 0:
             return 0
         gen = synthetic.confident_case if args.distribution == "conf" else synthetic.diffuse_case
+        if args.workload == "c4":
+            import numpy as np
+            from oracle import hist_oracle
+            lab, prd = synthetic.validation_maps(1, H, W, seed=1234 + 400)
+            l, p = lab.numpy(), prd.numpy()
+            ts = []
+            for i in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                hist_oracle.validation_confusion(l, p, 19, 255)
+                if i >= args.warmup:
+                    ts.append(time.perf_counter() - t0)
+            t = sum(ts) / len(ts)
+            val = H * W / t / 1e6
+            print(json.dumps({
+                "impl": "reference", "metric": "confusion_matrix_mpix_per_s", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": {"workload": f"c4: {desc}"},
+                "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                 "sample": "one 1024x2048 map per step; oracle/hist_oracle.py numpy restatement (np.bincount is single-threaded)"},
+                "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
         cfg_id = {"c1": 1, "c2": 2, "c3": 3, "c5": 5}[args.workload]
         probas, labels = gen(min(imgs, 4), H, W, seed=1234 + 100 * cfg_id)
         per_image = per_image_n1 or world > 1

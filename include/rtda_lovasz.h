@@ -63,7 +63,7 @@ const char *rtda_error_string(int code);
  *
  * Pixels whose label equals `ignore` (when has_ignore) or lies outside [0, C)
  * take no part (lovasz_loss.py:157-161); the number of out-of-range labels is
- * added to *label_errors so a caller can raise the reference's IndexError.
+ * reported in *label_errors so a caller can raise the reference's IndexError.
  */
 
 /* Bytes of scratch rtda_lovasz_fwd needs for this shape. */
@@ -84,13 +84,17 @@ int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t
  *   class_present [G][C] i32   1 where the class has a valid foreground pixel
  *   n_present     [G]    i32   K of each group
  *   group_loss    [G]    fp32  loss of each group (image); may be NULL
- *   label_errors  [1]    i32   += number of labels outside [0,C) and != ignore
+ *   label_errors  [1]    i32   number of labels outside [0,C) and != ignore; may be NULL
+ *   packed        [2+2C] f64   partials for a batch sharded over ranks (per_image): {sum of group
+ *                 losses, G, per-class sums of class_loss, per-class sums of class_present};
+ *                 one all-reduce(sum) of this buffer gives the global mean; may be NULL
  */
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
                     void *ws, size_t ws_bytes,
                     float *unit_grad, float *loss, float *class_loss, int32_t *class_present,
-                    int32_t *n_present, float *group_loss, int32_t *label_errors, void *stream);
+                    int32_t *n_present, float *group_loss, int32_t *label_errors, double *packed,
+                    void *stream);
 
 /* Backward: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) for present
  * classes, 0 elsewhere (the autograd of lovasz_loss.py:19-44,180); every element

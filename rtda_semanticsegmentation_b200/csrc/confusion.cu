@@ -17,7 +17,7 @@ namespace rtda {
 
 constexpr int kCmThreads = 256;
 constexpr int kCmWarps = kCmThreads / 32;
-constexpr int kCmUnroll = 4;
+constexpr int kCmUnroll = 8;
 
 // mode 0: one private histogram per warp; mode 1: one per block (shared atomics);
 // mode 2: no shared histogram (global atomics), for very large n_class.
@@ -134,8 +134,9 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
                             int has_ignore, int64_t *hist, cudaStream_t st) {
     size_t smem = 0;
     const int mode = cm_mode(n_class, &smem);
+    // few, persistent blocks: every block ends with up to n_class^2 atomics into the int64 matrix
     long long grid = (n + kCmThreads * kCmUnroll - 1) / (kCmThreads * kCmUnroll);
-    const long long cap = 8ll * sm_count();
+    const long long cap = 2ll * sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto *h = reinterpret_cast<unsigned long long *>(hist);
@@ -175,7 +176,7 @@ static int launch_confusion_argmax(const float *logits, const void *labels, long
     const int mode = cm_mode(n_class, &smem);
     const long long n = B * HW;
     long long grid = (n + kCmThreads - 1) / kCmThreads;
-    const long long cap = 16ll * sm_count();
+    const long long cap = 4ll * sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto *h = reinterpret_cast<unsigned long long *>(hist);

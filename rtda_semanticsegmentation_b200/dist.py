@@ -76,20 +76,30 @@ def sharded_per_image_mean(group_loss, class_loss, class_present, group=None):
 
 
 def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None):
-    """per_image=True Lovasz-Softmax over a batch sharded across ranks: each rank
-    passes its own images; every rank gets the global loss; gradients stay local."""
+    """per_image=True Lovasz-Softmax over a batch sharded across ranks: each rank passes its own
+    images; every rank gets the global loss; gradients stay local.  The finalize kernel writes the
+    partial buffer ``[sum of image losses, image count, class loss sums, class presence counts]``
+    and the autograd Function all-reduces it once (csrc/lovasz.cu k_finalize, lovasz_loss.py)."""
     from .lovasz_loss import lovasz_softmax
 
-    b_local = probas_local.size(0)
-    loss_local, outs = lovasz_softmax(probas_local, labels_local, per_image=True, ignore=ignore, return_outputs=True)
-    # loss_local is the mean over the local images; its sum over images carries the autograd graph
-    local_sum = loss_local * float(b_local)
-    packed = pack_partials(outs.group_loss, outs.class_loss, outs.class_present)
-    loss, packed = ShardedMeanOfImages.apply(local_sum, packed, group)
-    c = outs.class_loss.size(-1)
-    counts = packed[2 + c:]
-    stats = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
-    return loss, stats
+    loss, outs = lovasz_softmax(probas_local, labels_local, per_image=True, ignore=ignore, return_outputs=True,
+                                shard_group=True if group is None else group)
+    return loss, _ShardStats(outs, probas_local.size(1))
+
+
+class _ShardStats(dict):
+    """Lazily evaluated logging statistics of a sharded forward (device tensors, no sync)."""
+
+    def __init__(self, outs, c):
+        super().__init__()
+        self._outs, self._c = outs, c
+
+    def __missing__(self, key):
+        packed, c = self._outs.packed, self._c
+        counts = packed[2 + c:]
+        vals = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
+        self.update(vals)
+        return vals[key]
 
 
 def all_reduce_confusion(hist: torch.Tensor, group=None) -> torch.Tensor:

@@ -46,6 +46,7 @@ __all__ = [
     "mean",
     "isnan",
     "LovaszOutputs",
+    "release_workspaces",
 ]
 
 
@@ -74,16 +75,39 @@ def mean(l, ignore_nan=False, empty=0):
 
 
 class LovaszOutputs:
-    """Side outputs of the last forward (device tensors, no synchronisation)."""
+    """Side outputs of a forward (device tensors, created lazily as views of one small buffer;
+    reading them never synchronises): ``class_loss`` [G,C] fp32, ``class_present`` [G,C] i32,
+    ``n_present`` [G] i32, ``group_loss`` [G] fp32, ``label_errors`` [1] i32, ``packed`` [2+2C] f64
+    (see include/rtda_lovasz.h; after a sharded forward ``packed`` holds the all-reduced sums)."""
 
-    __slots__ = ("class_loss", "class_present", "n_present", "group_loss", "label_errors")
+    def __init__(self, buf, groups, classes):
+        self._buf, self._g, self._c = buf, groups, classes
+        g, c = groups, classes
+        o = 8 * (2 + 2 * c)
+        self._off = dict(packed=(0, 2 + 2 * c, torch.float64), loss=(o, 1, torch.float32),
+                         label_errors=(o + 4, 1, torch.int32), n_present=(o + 8, g, torch.int32),
+                         group_loss=(o + 8 + 4 * g, g, torch.float32),
+                         class_present=(o + 8 + 8 * g, g * c, torch.int32),
+                         class_loss=(o + 8 + 8 * g + 4 * g * c, g * c, torch.float32))
 
-    def __init__(self, class_loss, class_present, n_present, group_loss, label_errors):
-        self.class_loss = class_loss
-        self.class_present = class_present
-        self.n_present = n_present
-        self.group_loss = group_loss
-        self.label_errors = label_errors
+    @staticmethod
+    def nbytes(groups, classes):
+        return 8 * (2 + 2 * classes) + 8 + 8 * groups + 8 * groups * classes
+
+    def ptr(self, name):
+        return self._buf.data_ptr() + self._off[name][0]
+
+    def _view(self, name):
+        off, n, dt = self._off[name]
+        return self._buf[off:off + n * dt.itemsize].view(dt)
+
+    packed = property(lambda self: self._view("packed"))
+    loss = property(lambda self: self._view("loss")[0])
+    label_errors = property(lambda self: self._view("label_errors"))
+    n_present = property(lambda self: self._view("n_present"))
+    group_loss = property(lambda self: self._view("group_loss"))
+    class_present = property(lambda self: self._view("class_present").view(self._g, self._c))
+    class_loss = property(lambda self: self._view("class_loss").view(self._g, self._c))
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -93,6 +117,27 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
             "(the reference's CPU implementation is restated only in oracle/ for testing)")
 
 
+# Scratch for rtda_lovasz_fwd is several hundred MB (two (key,payload) ping-pong buffers); it is
+# kept per (device, stream) instead of being re-allocated every step, which would fragment the
+# caching allocator and cost milliseconds of cudaMalloc on large batches.  Work on one stream is
+# ordered, so successive calls can share it.  release_workspaces() frees them.
+_workspaces = {}
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def _workspace(dev, stream_ptr, nbytes):
+    key = (dev.index, stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
 def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool):
     """Runs rtda_lovasz_fwd.  probas [B,C,H,W] fp32 contiguous, labels [B,H,W] contiguous."""
     lib = _lib.load()
@@ -100,40 +145,46 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
     hw = h * w
     groups = b if per_image else 1
     dev = probas.device
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        nbytes = _lib.ctypes.c_size_t(0)
-        _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, int(per_image), _lib.ctypes.byref(nbytes)),
-                   "rtda_lovasz_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-        unit = torch.empty(b * c * hw, dtype=torch.float32, device=dev) if need_grad else None
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        class_loss = torch.empty((groups, c), dtype=torch.float32, device=dev)
-        present = torch.empty((groups, c), dtype=torch.int32, device=dev)
-        n_present = torch.empty((groups,), dtype=torch.int32, device=dev)
-        group_loss = torch.empty((groups,), dtype=torch.float32, device=dev)
-        label_errors = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(lib.rtda_lovasz_fwd(
-            probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
-            b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
-            ws.data_ptr(), nbytes.value,
-            unit.data_ptr() if unit is not None else None, loss.data_ptr(), class_loss.data_ptr(),
-            present.data_ptr(), n_present.data_ptr(), group_loss.data_ptr(), label_errors.data_ptr(),
-            stream), "rtda_lovasz_fwd")
-    return loss, unit, LovaszOutputs(class_loss, present, n_present, group_loss, label_errors), ws
+    if torch.cuda.current_device() != dev.index:
+        torch.cuda.set_device(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    nbytes = _lib.ctypes.c_size_t(0)
+    _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, int(per_image), _lib.ctypes.byref(nbytes)),
+               "rtda_lovasz_workspace_bytes")
+    ws = _workspace(dev, stream, nbytes.value)
+    unit = torch.empty(b * c * hw, dtype=torch.float32, device=dev) if need_grad else None
+    outs = LovaszOutputs(torch.empty(LovaszOutputs.nbytes(groups, c), dtype=torch.uint8, device=dev), groups, c)
+    _lib.check(lib.rtda_lovasz_fwd(
+        probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
+        b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
+        ws.data_ptr(), nbytes.value,
+        unit.data_ptr() if unit is not None else None, outs.ptr("loss"), outs.ptr("class_loss"),
+        outs.ptr("class_present"), outs.ptr("n_present"), outs.ptr("group_loss"), outs.ptr("label_errors"),
+        outs.ptr("packed"), stream), "rtda_lovasz_fwd")
+    return outs.loss, unit, outs, ws
 
 
 class _LovaszSoftmaxFunction(torch.autograd.Function):
-    """autograd hook around rtda_lovasz_fwd / rtda_lovasz_bwd."""
+    """autograd hook around rtda_lovasz_fwd / rtda_lovasz_bwd.  With ``shard_group`` set
+    (per_image over a batch sharded across ranks) the forward adds ONE all-reduce(sum) of the
+    packed partials and returns the global mean; the backward needs no collective."""
 
     @staticmethod
-    def forward(ctx, probas, labels, ignore, per_image, holder):
+    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group):
         need_grad = bool(ctx.needs_input_grad[0])
         loss, unit, outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
         if holder is not None:
             holder.append(outs)
         ctx.shape = tuple(probas.shape)
         ctx.per_image = per_image
+        ctx.shard_scale = None
+        if shard_group is not None:
+            import torch.distributed as dist
+
+            packed = outs.packed
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=None if shard_group is True else shard_group)
+            loss = (packed[0] / packed[1]).float()
+            ctx.shard_scale = (float(probas.size(0)) / packed[1]).float()   # B_local / B_global, on the device
         if need_grad:
             ctx.save_for_backward(unit, outs.class_present, outs.n_present)
         return loss
@@ -145,14 +196,17 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
         b, c, h, w = ctx.shape
         lib = _lib.load()
         dev = unit.device
-        go = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous().view(1)
+        go = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
+        if ctx.shard_scale is not None:
+            go = go * ctx.shard_scale
         grad = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.rtda_lovasz_bwd(
-                go.data_ptr(), unit.data_ptr(), present.data_ptr(), n_present.data_ptr(),
-                b, c, h * w, int(ctx.per_image), grad.data_ptr(),
-                torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
-        return grad, None, None, None, None
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        _lib.check(lib.rtda_lovasz_bwd(
+            go.data_ptr(), unit.data_ptr(), present.data_ptr(), n_present.data_ptr(),
+            b, c, h * w, int(ctx.per_image), grad.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
+        return grad, None, None, None, None, None
 
 
 def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
@@ -174,21 +228,25 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
 
 
 def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
-                   validate_labels=False, return_outputs=False):
+                   validate_labels=False, return_outputs=False, shard_group=None):
     """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
     computes, lovasz_loss.py:185-200).
 
     probas [B,C,H,W] class probabilities (softmax output), labels [B,H,W] int.
     ``classes`` accepts 'present' and 'all'; the reference skips foreground-less
     classes unconditionally (:167-168) so both average over present classes.
+    ``shard_group`` (a process group, or True for the default group) with ``per_image=True``
+    treats ``probas`` as this rank's slice of a batch sharded over the ranks (see dist.py).
     """
     if classes not in ("present", "all"):
         raise ValueError("classes must be 'present' or 'all'")
     probas, labels = _as_kernel_inputs(probas, labels)
     if probas.numel() == 0:
         return probas.sum() * 0.0  # lovasz_loss.py:135-136
+    if shard_group is not None and not per_image:
+        raise ValueError("only per_image=True shards over ranks (global mode needs one sort over all pixels)")
     holder = []
-    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder)
+    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group)
     outs = holder[0]
     if validate_labels:
         bad = int(outs.label_errors.item())

@@ -23,6 +23,9 @@ __all__ = ["fast_hist", "per_class_iou", "confusion_matrix", "confusion_matrix_f
            "ConfusionMatrix", "mean_iou"]
 
 
+_INT_KINDS = {torch.int64: _lib.LABEL_I64, torch.uint8: _lib.LABEL_U8, torch.int32: _lib.LABEL_I32}
+
+
 def _device(device=None):
     if device is not None:
         return torch.device(device)
@@ -50,6 +53,18 @@ def confusion_matrix(labels, preds, n_class=19, ignore_index=255, out=None):
     (validation.py:102-107 + utils.py:78-87).  Returns a CUDA int64 [n,n] tensor;
     pass ``out`` to accumulate into an existing one."""
     lib = _lib.load()
+    if (out is not None and torch.is_tensor(labels) and torch.is_tensor(preds) and labels.is_cuda and preds.is_cuda
+            and labels.dtype in _INT_KINDS and preds.dtype in _INT_KINDS and labels.is_contiguous()
+            and preds.is_contiguous() and labels.numel() == preds.numel()):
+        # fast path of a validation loop: device maps, existing accumulator - one C call, no checks repeated
+        dev = labels.device
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        _lib.check(lib.rtda_confusion_accumulate(
+            labels.data_ptr(), _INT_KINDS[labels.dtype], preds.data_ptr(), _INT_KINDS[preds.dtype], labels.numel(), n_class,
+            0 if ignore_index is None else int(ignore_index), int(ignore_index is not None), out.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream), "rtda_confusion_accumulate")
+        return out
     dev = labels.device if torch.is_tensor(labels) and labels.is_cuda else _device()
     labels = _as_device_ints(labels, dev)
     preds = _as_device_ints(preds, dev)
