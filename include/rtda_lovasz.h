@@ -62,8 +62,9 @@ const char *rtda_error_string(int code);
  * (the composition SURVEY.md 0.2 defines).  G = per_image ? B : 1 groups.
  *
  * Pixels whose label equals `ignore` (when has_ignore) or lies outside [0, C)
- * take no part (lovasz_loss.py:157-161); the number of out-of-range labels is
- * reported in *label_errors so a caller can raise the reference's IndexError.
+ * take no part (lovasz_loss.py:157-161): they are dropped before the sort and
+ * their gradient is 0.  The number of out-of-range labels is reported in
+ * *label_errors so a caller can raise the reference's IndexError.
  */
 
 /* Bytes of scratch rtda_lovasz_fwd needs for this shape. */
@@ -77,8 +78,11 @@ int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t
 /* Forward.  Outputs:
  *   unit_grad     [G][C][n] fp32, n = B*HW/G: d(sum of present class losses of the
  *                 group)/d(probas) for grad_out = 1 before the 1/K and 1/G factors,
- *                 i.e. -g_rank * sgn(fg - p); rows of absent classes are NOT written.
- *                 May be NULL (loss only, e.g. under torch.no_grad()).
+ *                 i.e. -g_rank * sgn(fg - p); rows of absent classes and ignored pixels
+ *                 are NOT written.  May be NULL (loss only, e.g. under torch.no_grad()).
+ *   codes         [B*HW] u8, 4-byte aligned: the class of every pixel, 255 = ignored or
+ *                 out of range; required with unit_grad (the backward reads both), else
+ *                 may be NULL.
  *   loss          [1]    fp32  the scalar loss (0 when nothing is valid)
  *   class_loss    [G][C] fp32  per-class Lovasz losses (0 where absent)
  *   class_present [G][C] i32   1 where the class has a valid foreground pixel
@@ -92,16 +96,17 @@ int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
                     void *ws, size_t ws_bytes,
-                    float *unit_grad, float *loss, float *class_loss, int32_t *class_present,
-                    int32_t *n_present, float *group_loss, int32_t *label_errors, double *packed,
-                    void *stream);
+                    float *unit_grad, uint8_t *codes, float *loss, float *class_loss,
+                    int32_t *class_present, int32_t *n_present, float *group_loss,
+                    int32_t *label_errors, double *packed, void *stream);
 
-/* Backward: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) for present
- * classes, 0 elsewhere (the autograd of lovasz_loss.py:19-44,180); every element
- * of grad_probas [B][C][HW] is written.  grad_out is a DEVICE scalar. */
-int rtda_lovasz_bwd(const float *grad_out, const float *unit_grad, const int32_t *class_present,
-                    const int32_t *n_present, int64_t B, int C, int64_t HW, int per_image,
-                    float *grad_probas, void *stream);
+/* Backward: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) at valid pixels of
+ * present classes, 0 elsewhere (the autograd of lovasz_loss.py:19-44,180); every element
+ * of grad_probas [B][C][HW] is written.  grad_out is a DEVICE scalar; unit_grad, codes,
+ * class_present and n_present are the forward's outputs. */
+int rtda_lovasz_bwd(const float *grad_out, const float *unit_grad, const uint8_t *codes,
+                    const int32_t *class_present, const int32_t *n_present, int64_t B, int C,
+                    int64_t HW, int per_image, float *grad_probas, void *stream);
 
 /* ---- Confusion matrix -----------------------------------------------------
  * hist[t * n_class + p] += 1 for every pixel with label t != ignore,

@@ -153,15 +153,17 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
                "rtda_lovasz_workspace_bytes")
     ws = _workspace(dev, stream, nbytes.value)
     unit = torch.empty(b * c * hw, dtype=torch.float32, device=dev) if need_grad else None
+    codes = torch.empty(b * hw, dtype=torch.uint8, device=dev) if need_grad else None
     outs = LovaszOutputs(torch.empty(LovaszOutputs.nbytes(groups, c), dtype=torch.uint8, device=dev), groups, c)
     _lib.check(lib.rtda_lovasz_fwd(
         probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
         b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
         ws.data_ptr(), nbytes.value,
-        unit.data_ptr() if unit is not None else None, outs.ptr("loss"), outs.ptr("class_loss"),
+        unit.data_ptr() if unit is not None else None, codes.data_ptr() if codes is not None else None,
+        outs.ptr("loss"), outs.ptr("class_loss"),
         outs.ptr("class_present"), outs.ptr("n_present"), outs.ptr("group_loss"), outs.ptr("label_errors"),
         outs.ptr("packed"), stream), "rtda_lovasz_fwd")
-    return outs.loss, unit, outs, ws
+    return outs.loss, (unit, codes), outs, ws
 
 
 class _LovaszSoftmaxFunction(torch.autograd.Function):
@@ -172,7 +174,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probas, labels, ignore, per_image, holder, shard_group):
         need_grad = bool(ctx.needs_input_grad[0])
-        loss, unit, outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
+        loss, (unit, codes), outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
         if holder is not None:
             holder.append(outs)
         ctx.shape = tuple(probas.shape)
@@ -186,13 +188,13 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
             loss = (packed[0] / packed[1]).float()
             ctx.shard_scale = (float(probas.size(0)) / packed[1]).float()   # B_local / B_global, on the device
         if need_grad:
-            ctx.save_for_backward(unit, outs.class_present, outs.n_present)
+            ctx.save_for_backward(unit, codes, outs.class_present, outs.n_present)
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        unit, present, n_present = ctx.saved_tensors
+        unit, codes, present, n_present = ctx.saved_tensors
         b, c, h, w = ctx.shape
         lib = _lib.load()
         dev = unit.device
@@ -203,7 +205,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
         _lib.check(lib.rtda_lovasz_bwd(
-            go.data_ptr(), unit.data_ptr(), present.data_ptr(), n_present.data_ptr(),
+            go.data_ptr(), unit.data_ptr(), codes.data_ptr(), present.data_ptr(), n_present.data_ptr(),
             b, c, h * w, int(ctx.per_image), grad.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
         return grad, None, None, None, None, None

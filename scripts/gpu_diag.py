@@ -29,7 +29,7 @@ def stage_check(probas, labels, ignore=255, per_image=False):
     L = layout(b, c, hw, per_image)
     p = probas.cuda().contiguous()
     l = labels.cuda().contiguous()
-    loss, unit, outs, ws = _forward_native(p, l, ignore, per_image, True)
+    loss, (unit, codes_t), outs, ws = _forward_native(p, l, ignore, per_image, True)
     torch.cuda.synchronize()
     wsn = ws.cpu().numpy()
     G = b if per_image else 1
@@ -39,7 +39,7 @@ def stage_check(probas, labels, ignore=255, per_image=False):
     ln = labels.numpy().reshape(G, n)
     valid = (ln != ignore) & (ln >= 0) & (ln < c)
     ok = True
-    codes = wsn[L["codes"]:L["codes"] + G * n].reshape(G, n)
+    codes = codes_t.cpu().numpy().reshape(G, n)
     want_codes = np.where(valid, ln, 255).astype(np.uint8)
     print("codes ok:", np.array_equal(codes, want_codes)); ok &= np.array_equal(codes, want_codes)
     hist = wsn[L["hist"]:L["hist"] + S * 4 * 256 * 4].view(np.uint32).reshape(S, 4, 256)
@@ -51,9 +51,9 @@ def stage_check(probas, labels, ignore=255, per_image=False):
             pc = pn[g, :, cc, :].reshape(n)
             fg = valid[g] & (ln[g] == cc)
             err = np.abs(fg.astype(np.float32) - pc).astype(np.float32)
-            key = ~np.where(valid[g], err.view(np.uint32), 0).astype(np.uint32)
+            key = (~err.view(np.uint32)).astype(np.uint32)
             for ps in range(4):
-                want = np.bincount((key >> (8 * ps)) & 255, minlength=256)
+                want = np.bincount((key[valid[g]] >> (8 * ps)) & 255, minlength=256)
                 if not np.array_equal(want, hist[s, ps]):
                     print(f"hist mismatch seg {s} pass {ps}: diff at", np.nonzero(want != hist[s, ps])[0][:8]); ok = False
             if segfg[s] != fg.sum():
@@ -64,10 +64,12 @@ def stage_check(probas, labels, ignore=255, per_image=False):
             pay = (fg.astype(np.uint32) << 31) | (np.arange(n, dtype=np.uint32))
             negb = ((fg.astype(np.float32) - pc) < 0) & valid[g]
             pay |= negb.astype(np.uint32) << 30
-            order = np.argsort(key & 0xFFFFFF, kind="stable")
+            vi = np.nonzero(valid[g])[0]                       # ignored pixels are dropped by pass 0
+            order = vi[np.argsort(key[vi] & 0xFFFFFF, kind="stable")]
             want_pairs = (key[order].astype(np.uint64) << 32) | pay[order].astype(np.uint64)
-            if not np.array_equal(want_pairs, bufa[s]):
-                bad = np.nonzero(want_pairs != bufa[s])[0]
+            got_pairs = bufa[s][:len(vi)]
+            if not np.array_equal(want_pairs, got_pairs):
+                bad = np.nonzero(want_pairs != got_pairs)[0]
                 print(f"buf_a mismatch seg {s}: {len(bad)} of {n}, first at {bad[:5]}"); ok = False
     want = c_oracle.lovasz(probas.numpy(), labels.numpy(), ignore, per_image)
     print("loss", float(loss), "oracle", float(want["loss"]))
