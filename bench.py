@@ -173,28 +173,54 @@ def bench_confusion(args, rank, local_rank, world):
     for i in range(warmup):
         cm.update(*maps[i % n_sets])
     cm.reset()
-    _lib.profile_enable(True)
-    _lib.profile_read()
+    # one CUDA graph holding the n_sets per-map update calls (a validation loop's launch pattern
+    # without the ~19 us of Python per call); eager launches if capture is not possible
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                cm.update(*maps[0])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for l, p in maps:
+                    cm.update(l, p)
+            cm.reset()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed, timing eager launches: {e!r}", file=sys.stderr)
+            graph = None
+    steps = args.steps if graph is None else max(n_sets, args.steps // n_sets * n_sets)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        cm.update(*maps[i % n_sets])
+    if graph is not None:
+        for i in range(steps // n_sets):
+            graph.replay()
+    else:
+        for i in range(steps):
+            cm.update(*maps[i % n_sets])
     cm.all_reduce()
     e1.record()
     sync()
     clocks = sampler.stop() if rank == 0 else None
-    stages = _lib.profile_read()
-    _lib.profile_enable(False)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = float(t.item()) / steps
     value = world * px / (ms_step * 1e-3) / 1e6
     total = int(cm.compute().sum())
+    # per-launch kernel time from the library's CUDA events, eager launches
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    for i in range(args.steps):
+        cm.update(*maps[i % n_sets])
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
 
     # end to end through the reference signature: numpy maps on the host -> fast_hist -> numpy matrix
     host = [(l.cpu().numpy().ravel(), p.cpu().numpy().ravel()) for l, p in maps[:3]]
@@ -215,10 +241,11 @@ def bench_confusion(args, rank, local_rank, world):
     per = k_ms / max(k_n, 1)
     achieved = CM_BYTES_PER_PX * px / (per * 1e-3) / 1e9
     line = {
-        "metric": "confusion_matrix_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "metric": "confusion_matrix_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": f"c4: {desc}", "classes": 19, "ignore": 255, "maps_per_step": 1,
+                   "launch": "cuda_graph replay of 10 per-map update calls" if graph is not None else "eager",
                    "l2_policy": f"{n_sets} distinct map pairs ({n_sets * px * 16 >> 20} MiB > 126 MiB L2) rotated every step",
                    "counted_pixels": total},
         "clocks": clocks,
@@ -259,6 +286,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--distribution", default="conf", choices=["conf", "diffuse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -366,9 +394,32 @@ def main():
         step(*sets[i % n_sets])
     barrier()
 
-    # ---- timed region 1: device-resident inputs, per-kernel events on
-    _lib.profile_enable(True)
-    _lib.profile_read()
+    # ---- CUDA graphs of one fwd+bwd per input set (single GPU): the launch path of the timed region
+    # is then free of host jitter.  Falls back to eager launches if capture is not possible.
+    graphs = None
+    if world == 1 and not args.no_graph:
+        try:
+            graphs = []
+            side = torch.cuda.Stream(dev)
+            for p, l in sets:
+                pin = p.detach().requires_grad_(True)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        crit(pin, l).backward()
+                        pin.grad = None
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    gl = crit(pin, l)
+                    gl.backward()
+                graphs.append((g, gl, pin))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed, timing eager launches: {e!r}", file=sys.stderr)
+            graphs = None
+
+    # ---- timed region 1: device-resident inputs
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -376,21 +427,38 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     host_t0 = time.perf_counter()
-    for i in range(args.steps):
-        loss, grad = step(*sets[i % n_sets])
+    if graphs is not None:
+        for i in range(args.steps):
+            graphs[i % n_sets][0].replay()
+        loss = graphs[(args.steps - 1) % n_sets][1]
+    else:
+        for i in range(args.steps):
+            loss, grad = step(*sets[i % n_sets])
     host_ms_step = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host enqueue time, no sync inside
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    stages = _lib.profile_read()
-    _lib.profile_enable(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * px_step / (ms_step * 1e-3) / 1e6
     loss_value = float(loss.item())
+
+    # ---- timed region 1b: the same steps launched eagerly with the library's per-launch CUDA events on
+    # (kernel table of the roofline; also the eager step time)
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(*sets[i % n_sets])
+    e1.record()
+    barrier()
+    eager_ms_step = e0.elapsed_time(e1) / args.steps
+    stages = _lib.profile_read()
+    _lib.profile_enable(False)
 
     # ---- timed region 2: end to end from pinned host buffers.  Every step's probas + labels are
     # copied host -> device inside the region (double-buffered on a side stream so the copy of step
@@ -455,7 +523,7 @@ def main():
         per = ms / max(cnt, 1)
         ob = own_bytes.get(name)
         kernels.append({"name": name, "launches": int(cnt), "ms_per_launch": round(per, 5),
-                        "share_of_step": round(ms / args.steps / ms_step, 4),
+                        "share_of_step": round(ms / args.steps / eager_ms_step, 4),
                         "own_gbs": round(ob / (per * 1e-3) / 1e9, 1) if ob and per > 0 else None,
                         "own_frac_of_peak": round(ob / (per * 1e-3) / 1e9 / peak, 4) if ob and per > 0 else None})
     kernels.sort(key=lambda k: -k["share_of_step"])
@@ -465,12 +533,13 @@ def main():
     line = {
         "metric": "lovasz_softmax_fwd_bwd_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "host_enqueue_ms_per_step": host_ms_step,
-        "gap_ms_per_step": gaps[0] / args.steps, "higher_is_better": True,
+        "eager_ms_per_step": eager_ms_step, "eager_gap_ms_per_step": gaps[0] / args.steps, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: {desc}" + ("" if world == 1 else f"; per rank {imgs}x{C}x{H}x{W}, per_image=True sharded over {world} ranks, 1 all-reduce of 40 doubles"),
             "classes": C, "ignore": 255, "per_image": per_image, "distribution": "D_" + args.distribution,
-            "labels": "int64", "l2_policy": f"{n_sets} distinct input sets ({n_sets * set_bytes >> 20} MiB > 126 MiB L2) rotated every step",
+            "labels": "int64", "launch": "cuda_graph replay of the public fwd+bwd call (one graph per input set)" if graphs is not None else "eager",
+            "l2_policy": f"{n_sets} distinct input sets ({n_sets * set_bytes >> 20} MiB > 126 MiB L2) rotated every step",
             "loss": loss_value,
         },
         "clocks": clocks,

@@ -15,7 +15,7 @@
 
 namespace rtda {
 
-constexpr int kCmThreads = 256;
+constexpr int kCmThreads = 1024;  // one block per SM, 32 warps: the kernel is latency-bound at 2 Mpx per call (profiles/)
 constexpr int kCmWarps = kCmThreads / 32;
 constexpr int kCmUnroll = 8;
 
@@ -123,7 +123,7 @@ k_confusion_argmax(const float *__restrict__ logits, const LabelT *__restrict__ 
 
 static int cm_mode(int n_class, size_t *smem) {
     const size_t nb = (size_t)n_class * n_class * sizeof(u32);
-    if (nb * kCmWarps <= 64 * 1024) { *smem = nb * kCmWarps; return 0; }
+    if (nb * kCmWarps <= 96 * 1024) { *smem = nb * kCmWarps; return 0; }
     if (nb <= 160 * 1024) { *smem = nb; return 1; }
     *smem = 0;
     return 2;
@@ -134,9 +134,10 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
                             int has_ignore, int64_t *hist, cudaStream_t st) {
     size_t smem = 0;
     const int mode = cm_mode(n_class, &smem);
-    // few, persistent blocks: every block ends with up to n_class^2 atomics into the int64 matrix
+    // one persistent 1024-thread block per SM: all loads of a block's share are in flight at once,
+    // and every block ends with at most n_class^2 atomics into the int64 matrix
     long long grid = (n + kCmThreads * kCmUnroll - 1) / (kCmThreads * kCmUnroll);
-    const long long cap = 2ll * sm_count();
+    const long long cap = sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto *h = reinterpret_cast<unsigned long long *>(hist);
@@ -176,7 +177,7 @@ static int launch_confusion_argmax(const float *logits, const void *labels, long
     const int mode = cm_mode(n_class, &smem);
     const long long n = B * HW;
     long long grid = (n + kCmThreads - 1) / kCmThreads;
-    const long long cap = 4ll * sm_count();
+    const long long cap = 2ll * sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     auto *h = reinterpret_cast<unsigned long long *>(hist);
