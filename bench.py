@@ -176,7 +176,7 @@ def bench_confusion(args, rank, local_rank, world):
     # one CUDA graph holding the n_sets per-map update calls (a validation loop's launch pattern
     # without the ~19 us of Python per call); eager launches if capture is not possible
     graph = None
-    if not args.no_graph:
+    if world == 1 and not args.no_graph:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -397,6 +397,8 @@ def main():
     # ---- CUDA graphs of one fwd+bwd per input set (single GPU): the launch path of the timed region
     # is then free of host jitter.  Falls back to eager launches if capture is not possible.
     graphs = None
+    # single GPU only: capturing the NCCL all-reduce of the sharded path hung in round 1 (2 ranks),
+    # so N > 1 times eager launches
     if world == 1 and not args.no_graph:
         try:
             graphs = []
