@@ -500,6 +500,12 @@ def main():
         return 0
 
     peak, peak_src = peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except OSError:
+        pass
     algo_bytes = ALGO_BYTES_PER_PX * px_step
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     # per-kernel compulsory traffic of each stage's own job (bytes per launch), for the kernel table
@@ -551,7 +557,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic["bytes_per_step"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else None, "algorithmic_bytes": algo_bytes,
+            "peak_source": peak_src,
             "what": "whole fwd+bwd step: 160 B/px algorithmic bytes x pixels / CUDA-event step time (the sort passes move ~1.2 KB/px, so the algorithmic fraction is far below each kernel's own DRAM fraction)",
             "dominant_kernel": dom["name"], "dominant_share_of_step": dom["share_of_step"],
             "dominant_own_gbs": dom["own_gbs"], "dominant_own_frac_of_peak": dom["own_frac_of_peak"],

@@ -192,11 +192,12 @@ def test_lovasz_grad_free_function():
     assert rtda.lovasz_grad(torch.ones(1, device="cuda")).item() == 1.0
 
 
-@pytest.mark.parametrize("cfg", ["c1_global", "c2_global", "c2_per_image"])
+@pytest.mark.parametrize("cfg", ["c1_global", "c2_global", "c2_per_image", "c5_global", "c3_per_image"])
 def test_baseline_configs_full_size_bit_exact(cfg):
-    """BASELINE.json configs[0] and configs[1] at full size against the C oracle (seconds on CPU)."""
-    b = 1 if cfg == "c1_global" else 4
-    probas, labels = synthetic.confident_case(b, 512, 1024, seed=1234 + 100 * (1 if b == 1 else 2), device="cuda")
+    """BASELINE.json configs[0], [1], [4] and [2] (Lovasz part) at full size against the C oracle
+    (seconds on CPU): 1x, 4x, 8x19x512x1024 and 16x19x720x1280 per image."""
+    b, h, w = {"c1": (1, 512, 1024), "c2": (4, 512, 1024), "c5": (8, 512, 1024), "c3": (16, 720, 1280)}[cfg[:2]]
+    probas, labels = synthetic.confident_case(b, h, w, seed=1234 + 100 * int(cfg[1]), device="cuda")
     per_image = cfg.endswith("per_image")
     loss, grad = assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, per_image, tag=cfg)
     # size-independent invariants (SURVEY.md section 4)
@@ -211,3 +212,52 @@ def test_baseline_configs_full_size_bit_exact(cfg):
 def test_diffuse_distribution_full_size():
     probas, labels = synthetic.diffuse_case(1, 512, 1024, seed=1334, device="cuda")
     assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, False, tag="diffuse c1")
+
+
+@pytest.mark.parametrize("b,c,h,w", [(40, 19, 9, 11), (3500, 19, 2, 2), (700, 3, 1, 5)])
+def test_many_groups_per_image(b, c, h, w):
+    """per_image with hundreds / thousands of tiny images: many sort segments, more (image, class)
+    planes than gridDim.y allows, finalize without its shared-memory copy."""
+    g = torch.Generator().manual_seed(b + c)
+    probas = torch.softmax(torch.randn((b, c, h, w), generator=g) * 2, 1)
+    labels = torch.randint(0, c, (b, h, w), generator=g)
+    labels[torch.rand((b, h, w), generator=g) < 0.2] = 255
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, True, tag=f"{b} images")
+
+
+def test_hypothesis_invariants():
+    """Property tests of SURVEY.md section 4 invariants on random small problems: (i) zero gradient at
+    ignored pixels and in absent classes, (ii) sign pattern, (iii) sum |grad| == 1, plus oracle parity."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 3), st.integers(2, 12), st.integers(1, 40), st.integers(1, 40), st.integers(0, 2 ** 31 - 1),
+           st.floats(0.0, 0.6), st.booleans())
+    def run(b, c, h, w, seed, ign, per_image):
+        g = torch.Generator().manual_seed(seed)
+        probas = torch.softmax(torch.randn((b, c, h, w), generator=g) * 3, 1)
+        labels = torch.randint(0, c, (b, h, w), generator=g)
+        labels[torch.rand((b, h, w), generator=g) < ign] = 255
+        loss, grad = assert_matches_oracle(probas.numpy(), labels.numpy(), 255, per_image, tag="hypothesis")
+        lab = labels.numpy()
+        ignored = lab == 255
+        assert not grad.transpose(0, 2, 3, 1)[ignored].any()
+        groups = range(b) if per_image else [slice(None)]
+        for gi in groups:
+            gsel = grad[gi] if per_image else grad
+            lsel = lab[gi] if per_image else lab
+            present = [k for k in range(c) if (lsel == k).any()]
+            for k in range(c):
+                if k not in present:
+                    assert not (gsel[k] if per_image else gsel[:, k]).any()
+        if (~ignored).any():
+            onehot = np.zeros_like(grad, dtype=bool)
+            np.put_along_axis(onehot, np.where(ignored, 0, lab)[:, None], True, axis=1)
+            onehot &= ~ignored[:, None]
+            assert np.all(grad[onehot] <= 0) and np.all(grad[~onehot] >= 0)
+            if (probas.numpy() > 0).all() and (probas.numpy() < 1).all():
+                n_groups = sum(1 for i in range(b) if (lab[i] != 255).any()) if per_image else 1
+                want = n_groups / b if per_image else 1.0
+                assert np.abs(grad.astype(np.float64)).sum() == pytest.approx(want, abs=1e-4)
+
+    run()
