@@ -287,6 +287,9 @@ def main():
     ap.add_argument("--distribution", default="conf", choices=["conf", "diffuse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--hybrid", default="none", choices=["none", "fused", "unfused"],
+                    help="time CE + 0.5*Lovasz from LOGITS (train_lovasz.py:98-108): fused = rtda_hybrid_fwd/bwd, "
+                         "unfused = torch softmax + torch CE + LovaszSoftmax; not the BASELINE metric")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -371,10 +374,24 @@ def main():
     n_sets = max(2, min(6, -(-400 * 1024 * 1024 // set_bytes)))
     sets = []
     for i in range(n_sets):
-        p, l = gen(imgs, H, W, seed=1234 + 100 * cfg_id + rank + 1000 * i, device=dev)
+        if args.hybrid != "none":       # the hybrid step starts from logits
+            l = synthetic.blocky_labels(imgs, H, W, seed=1234 + 100 * cfg_id + rank + 1000 * i, device=dev)
+            p = synthetic.confident_logits(l, seed=1234 + 100 * cfg_id + rank + 1000 * i)
+        else:
+            p, l = gen(imgs, H, W, seed=1234 + 100 * cfg_id + rank + 1000 * i, device=dev)
         sets.append((p.contiguous(), l.contiguous()))
     px_step = imgs * H * W
-    crit = rtda.LovaszSoftmax(ignore=255, per_image=per_image)
+    lovasz = rtda.LovaszSoftmax(ignore=255, per_image=per_image)
+    fused = rtda.HybridCELovasz(ignore=255, lovasz_weight=0.5, per_image=per_image)
+    if args.hybrid != "none" and world > 1:
+        raise SystemExit("--hybrid is a single-GPU measurement")
+
+    def crit(x, l):
+        if args.hybrid == "fused":
+            return fused(x, l)
+        if args.hybrid == "unfused":
+            return torch.nn.functional.cross_entropy(x, l, ignore_index=255) + 0.5 * lovasz(torch.softmax(x, dim=1), l)
+        return lovasz(x, l)
 
     def step(p, l):
         p = p.detach().requires_grad_(True)
@@ -539,7 +556,8 @@ def main():
     gaps = stages.get("gaps_between_launches", (0.0, 0))
 
     line = {
-        "metric": "lovasz_softmax_fwd_bwd_mpix_per_s", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "metric": "lovasz_softmax_fwd_bwd_mpix_per_s" if args.hybrid == "none" else f"hybrid_ce_lovasz_fwd_bwd_mpix_per_s[{args.hybrid}]",
+        "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "host_enqueue_ms_per_step": host_ms_step,
         "eager_ms_per_step": eager_ms_step, "eager_gap_ms_per_step": gaps[0] / args.steps, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",

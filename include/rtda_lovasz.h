@@ -108,6 +108,27 @@ int rtda_lovasz_bwd(const float *grad_out, const float *unit_grad, const uint8_t
                     const int32_t *class_present, const int32_t *n_present, int64_t B, int C,
                     int64_t HW, int per_image, float *grad_probas, void *stream);
 
+/* ---- Hybrid cross-entropy + Lovasz from logits ------------
+ * What every caller computes around the loss (train_lovasz.py:98-105,120-127,280-289):
+ *     loss_ce     = CrossEntropyLoss(ignore_index)(logits, labels)
+ *     probas      = softmax(logits, dim=1)
+ *     loss_lovasz = LovaszSoftmax(ignore)(probas, labels)
+ * fused: softmax and the cross-entropy sum ride on the histogram kernel's read of the logits,
+ * and the backward produces d(go_ce*loss_ce + go_lov*loss_lovasz)/d(logits) in one kernel.
+ * probas [B][C][HW] fp32 is an OUTPUT of the forward (kept for the backward); n_valid [1] is the
+ * number of pixels the cross-entropy averages over.  The other arguments are those of
+ * rtda_lovasz_fwd / rtda_lovasz_bwd; grad_ce and grad_lovasz are DEVICE scalars. */
+int rtda_hybrid_fwd(const float *logits, const void *labels, int label_kind,
+                    int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
+                    void *ws, size_t ws_bytes,
+                    float *probas, float *unit_grad, uint8_t *codes, float *loss_lovasz, float *loss_ce,
+                    float *class_loss, int32_t *class_present, int32_t *n_present, float *group_loss,
+                    int32_t *label_errors, double *packed, int32_t *n_valid, void *stream);
+int rtda_hybrid_bwd(const float *grad_ce, const float *grad_lovasz, const float *probas,
+                    const float *unit_grad, const uint8_t *codes, const int32_t *class_present,
+                    const int32_t *n_present, const int32_t *n_valid, int64_t B, int C, int64_t HW,
+                    int per_image, float *grad_logits, void *stream);
+
 /* ---- Confusion matrix -----------------------------------------------------
  * hist[t * n_class + p] += 1 for every pixel with label t != ignore,
  * 0 <= t < n_class and 0 <= p < n_class (validation.py:102-107 + utils.py:78-87).

@@ -5,6 +5,7 @@ arman-rn/RTDA-SemanticSegmentation (losses/lovasz_loss.py and utils.py:62-116),
 behind the reference's own call boundary.  See DESIGN.md and INTEGRATION.md.
 """
 from . import _lib
+from .hybrid_loss import HybridCELovasz, hybrid_ce_lovasz
 from .lovasz_loss import (LovaszSoftmax, flatten_probas, isnan, lovasz_grad, lovasz_softmax,
                           lovasz_softmax_flat, mean)
 from .metrics import (ConfusionMatrix, confusion_matrix, confusion_matrix_from_logits, fast_hist,
@@ -13,7 +14,7 @@ from .metrics import (ConfusionMatrix, confusion_matrix, confusion_matrix_from_l
 __all__ = [
     "LovaszSoftmax", "lovasz_softmax", "lovasz_softmax_flat", "lovasz_grad", "flatten_probas", "mean", "isnan",
     "fast_hist", "per_class_iou", "mean_iou", "confusion_matrix", "confusion_matrix_from_logits",
-    "ConfusionMatrix", "build", "native_library_path",
+    "ConfusionMatrix", "HybridCELovasz", "hybrid_ce_lovasz", "build", "native_library_path",
 ]
 
 

@@ -29,6 +29,9 @@ SIGNATURES = {
     "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rtda_lovasz_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _int, _vp, _vp]),
+    "rtda_hybrid_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtda_hybrid_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "rtda_confusion_accumulate": (_int, [_vp, _int, _vp, _int, _i64, _int, _i64, _int, _vp, _vp]),
     "rtda_confusion_argmax_accumulate": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _vp, _vp]),
     "rtda_profile_enable": (_int, [_int]),

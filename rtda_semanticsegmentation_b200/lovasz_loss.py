@@ -85,14 +85,15 @@ class LovaszOutputs:
         g, c = groups, classes
         o = 8 * (2 + 2 * c)
         self._off = dict(packed=(0, 2 + 2 * c, torch.float64), loss=(o, 1, torch.float32),
-                         label_errors=(o + 4, 1, torch.int32), n_present=(o + 8, g, torch.int32),
-                         group_loss=(o + 8 + 4 * g, g, torch.float32),
-                         class_present=(o + 8 + 8 * g, g * c, torch.int32),
-                         class_loss=(o + 8 + 8 * g + 4 * g * c, g * c, torch.float32))
+                         label_errors=(o + 4, 1, torch.int32), loss_ce=(o + 8, 1, torch.float32),
+                         n_valid=(o + 12, 1, torch.int32), n_present=(o + 16, g, torch.int32),
+                         group_loss=(o + 16 + 4 * g, g, torch.float32),
+                         class_present=(o + 16 + 8 * g, g * c, torch.int32),
+                         class_loss=(o + 16 + 8 * g + 4 * g * c, g * c, torch.float32))
 
     @staticmethod
     def nbytes(groups, classes):
-        return 8 * (2 + 2 * classes) + 8 + 8 * groups + 8 * groups * classes
+        return 8 * (2 + 2 * classes) + 16 + 8 * groups + 8 * groups * classes
 
     def ptr(self, name):
         return self._buf.data_ptr() + self._off[name][0]
@@ -104,6 +105,8 @@ class LovaszOutputs:
     packed = property(lambda self: self._view("packed"))
     loss = property(lambda self: self._view("loss")[0])
     label_errors = property(lambda self: self._view("label_errors"))
+    loss_ce = property(lambda self: self._view("loss_ce")[0])        # hybrid path only
+    n_valid = property(lambda self: self._view("n_valid"))            # hybrid path only
     n_present = property(lambda self: self._view("n_present"))
     group_loss = property(lambda self: self._view("group_loss"))
     class_present = property(lambda self: self._view("class_present").view(self._g, self._c))
