@@ -72,8 +72,18 @@ int rtda_lovasz_workspace_bytes(int64_t B, int C, int64_t HW, int per_image, siz
 
 /* Debug / test aid: byte offsets of the regions inside the workspace, in the order
  * {hist, fghist, tickets, desc32, desc64, zero_end, base, fgbase, seg_fg, codes,
- *  partial, buf_a, buf_b, total, segments S, tiles per segment T}.  offsets[16]. */
+ *  partial, buf_a, buf_b, total, segments S, tiles per segment T,
+ *  fb_flag (u32 [S]: 1 where the segment was sorted by the LSD radix path), nb (u32 [S] buckets),
+ *  cursor (u64 [S][NBK]: elements | fg elements << 32 per bucket), table, partial_b,
+ *  level-1 tiles per segment T1, bucket regions per segment NBK, bucket capacity}.  offsets[24]. */
 int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t *offsets);
+
+/* Sort path of the forward: 0 (default) = sample-partitioned bucket sort, with a per-segment,
+ * device-side fallback to the LSD radix sort for key distributions it cannot split (massive exact
+ * ties); 1 = LSD radix sort for every segment.  Both produce bit-identical results (descending
+ * error, ties by ascending pixel index).  Process-wide; a test / benchmark aid.  The environment
+ * variable RTDA_SORT_PATH=lsd selects 1 at the first call. */
+int rtda_lovasz_set_sort_path(int path);
 
 /* Forward.  Outputs:
  *   unit_grad     [G][C][n] fp32, n = B*HW/G: d(sum of present class losses of the
@@ -151,7 +161,7 @@ int rtda_confusion_argmax_accumulate(const float *logits, const void *labels, in
  * last read into the caller's host arrays, and recycles the events.  Off by
  * default; meant for single-threaded benchmark use (the event list is global).
  * Stages: see rtda_profile_stage_name(0 .. RTDA_PROFILE_STAGES-1). */
-#define RTDA_PROFILE_STAGES 12
+#define RTDA_PROFILE_STAGES 16
 int rtda_profile_enable(int on);
 int rtda_profile_read(double *stage_ms_host, int64_t *stage_launches_host, int n_stages);
 const char *rtda_profile_stage_name(int stage);

@@ -26,6 +26,7 @@ SIGNATURES = {
     "rtda_error_string": (ctypes.c_char_p, [_int]),
     "rtda_lovasz_workspace_bytes": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "rtda_lovasz_debug_layout": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
+    "rtda_lovasz_set_sort_path": (_int, [_int]),
     "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rtda_lovasz_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _int, _vp, _vp]),
@@ -39,7 +40,7 @@ SIGNATURES = {
     "rtda_profile_stage_name": (ctypes.c_char_p, [_int]),
 }
 
-PROFILE_STAGES = 12
+PROFILE_STAGES = 16
 
 
 def profile_enable(on: bool) -> None:

@@ -24,8 +24,9 @@ namespace rtda {
 // Optional per-launch timing (profile.cu).  A ProfileScope brackets one launch with two
 // events on the launch stream when profiling is enabled; otherwise it does nothing.
 enum Stage {
-    kStageMemset = 0, kStageHist, kStageScan, kStagePass0, kStagePass1, kStagePass2, kStageRankLast,
-    kStageFinalize, kStageBwd, kStageConfusion, kStageConfusionArgmax, kStageOther
+    kStageMemset = 0, kStagePrep, kStageScan, kStagePass0, kStagePass1, kStagePass2, kStageRankLast,
+    kStageFinalize, kStageBwd, kStageConfusion, kStageConfusionArgmax, kStageOther,
+    kStageSplit, kStagePart, kStageLocal, kStageHistFb
 };
 bool profile_enabled();
 void profile_begin(int stage, cudaStream_t st);

@@ -47,6 +47,8 @@ __all__ = [
     "isnan",
     "LovaszOutputs",
     "release_workspaces",
+    "set_sort_path",
+    "segment_sort_paths",
 ]
 
 
@@ -139,6 +141,30 @@ def _workspace(dev, stream_ptr, nbytes):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
     return ws
+
+
+SORT_PATHS = {"bucket": 0, "lsd": 1}
+
+
+def set_sort_path(path: str) -> None:
+    """Selects how the forward sorts (process-wide; a test / benchmark aid): ``"bucket"`` (default) is
+    the sample-partitioned bucket sort with a per-segment device-side fallback to the LSD radix sort,
+    ``"lsd"`` forces the LSD radix sort everywhere.  Results are bit-identical."""
+    _lib.check(_lib.load().rtda_lovasz_set_sort_path(SORT_PATHS[path]), "rtda_lovasz_set_sort_path")
+
+
+def segment_sort_paths(shape, per_image, stream=None):
+    """After a forward of ``shape`` = (B, C, H, W) on the current device/stream: int32 tensor [G, C],
+    1 where the (group, class) segment was sorted by the LSD radix path, 0 where the bucket path did it
+    (absent classes report 0).  Synchronises; debug / test aid."""
+    b, c, h, w = shape
+    o = (_lib.ctypes.c_size_t * 24)()
+    _lib.check(_lib.load().rtda_lovasz_debug_layout(b, c, h * w, int(per_image), o), "rtda_lovasz_debug_layout")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ws = _workspaces[(dev.index, torch.cuda.current_stream(dev).cuda_stream if stream is None else stream)]
+    groups = b if per_image else 1
+    torch.cuda.synchronize()
+    return ws[int(o[16]):int(o[16]) + 4 * groups * c].view(torch.int32).view(groups, c).clone()
 
 
 def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool):

@@ -16,7 +16,7 @@ from rtda_semanticsegmentation_b200.lovasz_loss import _forward_native  # noqa: 
 
 
 def layout(b, c, hw, per_image):
-    o = (ctypes.c_size_t * 16)()
+    o = (ctypes.c_size_t * 24)()
     _lib.check(_lib.load().rtda_lovasz_debug_layout(b, c, hw, int(per_image), o), "layout")
     names = ["hist", "fghist", "tickets", "desc32", "desc64", "zero_end", "base", "fgbase", "seg_fg", "codes",
              "partial", "buf_a", "buf_b", "total", "S", "T"]
