@@ -53,21 +53,31 @@ __device__ __forceinline__ T block_excl_scan(T v, T *warp_tmp /*[NW]*/, T *total
     return woff + incl - v;
 }
 
+// Monotone re-parametrisation of the sort key in which softmax errors are smoothly distributed.
+// Ascending key = descending error.  Errors in [0.5, 1] come from |1 - p| with p small (a confident
+// miss) or from p itself close to 1: there 1 - err is exact in fp32 and spreads over many binades
+// while err is squeezed against 1, so tau follows the bits of 1 - err.  Errors below 0.5 follow the
+// bits of err (descending).  In tau the density is that of a log-scale histogram, which a
+// piecewise-linear map models well; in the raw key the last bin under err = 1 holds a spike.
+__device__ __forceinline__ u32 tau_of(u32 key) {
+    const u32 eb = ~key;                             // bits of the error
+    if (eb > 0x3F800000u) return 0u;                 // err > 1 or NaN (garbage probabilities): first
+    return eb >= 0x3F000000u ? __float_as_uint(__fsub_rn(1.0f, __uint_as_float(eb))) : 0x7E000000u - eb;
+}
+
 // Monotone map key -> position in the sampled cumulative distribution, in units of buckets, 16.16 fixed
-// point: the 11-bit key prefix (sign / top exponent bits are constant for errors in [0,1]) selects a
-// table interval [tab[p], tab[p+1]), the low 19 key bits interpolate inside it.  Integer part = bucket,
-// fractional part = position inside the bucket (level 2 turns it into a slot).
+// point: the top 12 bits of tau select a table interval [tab[p], tab[p+1]), its low 19 bits
+// interpolate inside it.  Integer part = bucket, fractional part = position inside the bucket
+// (level 2 turns it into a fine slot).
 __device__ __forceinline__ u32 cdf_pos(u32 key, const u32 *tab, u32 xmax) {
-    if (key < 0xC0000000u) return 0u;     // errors > 2 / NaN (garbage probabilities): first bucket, first slot
-    const u32 p = (key >> 19) - 0x1800u;
+    const u32 tau = tau_of(key);
+    const u32 p = tau >> 19;                         // <= 0x7E0 << 1 = 4032
     const u32 x0 = tab[p], dx = tab[p + 1] - x0;
-    const u32 x = x0 + __umulhi(key << 13, dx);                 // (low19 * dx) >> 19
+    const u32 x = x0 + __umulhi(tau << 13, dx);      // (low19 * dx) >> 19
     return x < xmax ? x : xmax;
 }
 
-__device__ __forceinline__ u32 table_bin(u32 key) {
-    return key < 0xC0000000u ? 0u : (key >> 19) - 0x1800u;
-}
+__device__ __forceinline__ u32 table_bin(u32 key) { return tau_of(key) >> 19; }
 
 // ---------------------------------------------------------------------------
 // k_split: sample histogram -> cumulative map of one segment.  gridDim.y blocks share a segment:
@@ -87,7 +97,7 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         if (tid == 0 && blockIdx.y == 0) nb_out[seg] = 0;
         return;
     }
-    if (force_lsd || geo.n >= (1ll << 29)) {      // bit 29 of the payload marks the first element of a slot in k_local
+    if (force_lsd) {
         if (tid == 0 && blockIdx.y == 0) { nb_out[seg] = 0; fb_flag[seg] = 1u; *fb_any = 1u; }
         return;
     }
@@ -109,10 +119,10 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
                 const u32 i = i0 + k;
                 if (i >= n) break;
                 const u32 code = cg[i];
+                const u32 bi = i / HW, hw = i - bi * HW;
+                const float p = probas[(((size_t)g * geo.Bg + bi) * geo.C + c) * (size_t)HW + hw];   // independent of the code load
                 if (code == 255u) continue;
                 ++mvalid;
-                const u32 bi = i / HW, hw = i - bi * HW;
-                const float p = probas[(((size_t)g * geo.Bg + bi) * geo.C + c) * (size_t)HW + hw];
                 u32 neg;
                 const u32 key = error_key(p, true, code == c, &neg);
                 if (key == 0xFFFFFFFFu) continue;          // error exactly 0: never sorted
@@ -139,9 +149,12 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         if (tid == 0) s_mvalid = ld_relaxed(&gh[kTabBins]);
         __syncthreads();
     }
-    const u32 h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+    constexpr int kPerT = kTabBins / kSplitThreads;
+    u32 h[kPerT], hsum = 0;
+#pragma unroll
+    for (int k = 0; k < kPerT; ++k) { h[k] = hist[kPerT * tid + k]; hsum += h[k]; }
     u32 m_nz = 0;
-    const u32 excl = block_excl_scan<kSplitThreads / 32, u32>(h0 + h1, wtmp, &m_nz);
+    const u32 excl = block_excl_scan<kSplitThreads / 32, u32>(hsum, wtmp, &m_nz);
     u32 valid = 0;
     for (int k = 0; k < geo.C; ++k) valid += seg_fg[g * geo.C + k];
     const u32 mv = s_mvalid;
@@ -157,10 +170,12 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     u32 *tab = table + (size_t)seg * (kTabBins + 1);
     const u64 scale = (u64)NB << 16;
     const u64 denom = (u64)kPrior * m_nz + kTabBins;
-    const u64 c0 = (u64)kPrior * excl + 2u * tid;
-    const u64 c1 = c0 + (u64)kPrior * h0 + 1u;
-    tab[2 * tid] = (u32)((c0 * scale) / denom);
-    tab[2 * tid + 1] = (u32)((c1 * scale) / denom);
+    u64 cum = (u64)kPrior * excl + (u64)kPerT * tid;
+#pragma unroll
+    for (int k = 0; k < kPerT; ++k) {
+        tab[kPerT * tid + k] = (u32)((cum * scale) / denom);
+        cum += (u64)kPrior * h[k] + 1u;
+    }
     if (tid == 0) { tab[kTabBins] = (u32)scale; nb_out[seg] = NB; }
 }
 
@@ -187,8 +202,10 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     extern __shared__ __align__(16) unsigned char part_smem[];
     PartShared &sm = *reinterpret_cast<PartShared *>(part_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 seg = blockIdx.x / (u32)geo.T1;
-    const u32 tile = blockIdx.x - seg * (u32)geo.T1;
+    // a block takes kPTilesPerBlock consecutive tiles of one segment: the map is loaded once for them
+    const u32 bps = ((u32)geo.T1 + kPTilesPerBlock - 1) / kPTilesPerBlock;
+    const u32 seg = blockIdx.x / bps;
+    const u32 tile0 = (blockIdx.x - seg * bps) * kPTilesPerBlock;
     // other blocks of this kernel may raise the flag while this one starts: one thread decides for the block
     if (tid == 0) sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
     __syncthreads();
@@ -198,9 +215,16 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     u32 *sm_cnt = sm.arrays;
     u32 *sm_pre = sm.arrays + ((u32)geo.NBK + kPThreads - 1) / kPThreads * kPThreads;
     const u32 n = (u32)geo.n;
-    const u32 tile_base = tile * (u32)kPTile;
-    const u32 count = (n - tile_base < (u32)kPTile) ? n - tile_base : (u32)kPTile;
     const size_t seg_off = (size_t)seg * n;
+    {
+        const u32 *tsrc = table + (size_t)seg * (kTabBins + 1);
+        for (u32 k = tid; k < (u32)kTabBins + 1u; k += kPThreads) sm.tab[k] = tsrc[k];
+    }
+    for (u32 tile = tile0; tile < tile0 + kPTilesPerBlock; ++tile) {
+    const u32 tile_base = tile * (u32)kPTile;
+    if (tile_base >= n) break;
+    const u32 count = (n - tile_base < (u32)kPTile) ? n - tile_base : (u32)kPTile;
+    __syncthreads();          // the previous tile no longer uses the shared arrays (and the map is loaded)
 
     // per element: the key and one word of state {fg:31, neg:30, live:29, bucket:16..26, rank in (tile, bucket):0..12};
     // the pixel index is recomputed from the element's position in the tile
@@ -233,11 +257,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             hw += 32;
             while (hw >= HW) { hw -= HW; pp += wrap; }
         }
-        {
-            const u32 *tsrc = table + (size_t)seg * (kTabBins + 1);
-            for (u32 k = tid; k < (u32)kTabBins + 1u; k += kPThreads) sm.tab[k] = tsrc[k];
-            for (u32 b = tid; b < NB; b += kPThreads) sm_cnt[b] = 0;
-        }
+        for (u32 b = tid; b < NB; b += kPThreads) sm_cnt[b] = 0;
         float *ug = unit_grad ? unit_grad + seg_off : nullptr;
 #pragma unroll
         for (int j = 0; j < kPItems; ++j) {
@@ -298,8 +318,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 #pragma unroll
     for (int j = 0; j < kPItems; ++j)
         if (st[j] & kLive)
+            // payload while in shared memory: {fg, neg, bucket:12..22, position in the tile:0..11}
             sm.exch[sm_pre[(st[j] >> 16) & 0x7ffu] + (st[j] & 0x1fffu)] =
-                ((u64)key[j] << 32) | (st[j] & (kPayloadFg | kPayloadNeg)) | (i0 + 32 * j);
+                ((u64)key[j] << 32) | (st[j] & (kPayloadFg | kPayloadNeg)) | (((st[j] >> 16) & 0x7ffu) << 12) | (idx0 + 32 * j);
 
     bool overflow = false;
 #pragma unroll
@@ -333,31 +354,186 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         const u32 pos = k * kPThreads + tid;
         if (pos < total) {
             const u64 v = sm.exch[pos];
-            const u32 d = sm_cnt[cdf_pos((u32)(v >> 32), sm.tab, xmax) >> 16];
-            if (d != kNoDst) dst[d + pos] = v;
+            const u32 pl = (u32)v;
+            const u32 d = sm_cnt[(pl >> 12) & 0x7ffu];
+            // global payload: {fg, neg, pixel index in the segment}
+            if (d != kNoDst) dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & 0xfffu));
         }
+    }
     }
 }
 
 // ---------------------------------------------------------------------------
 // k_local: level 2.  One block per (segment, bucket), segment-major so that the 4-byte gradient
 // scatter of one segment stays inside one L2-resident plane.
+//
+// The fractional part of an element's cumulative position is its place inside the bucket.  Its top
+// bits select one of kFine / 2^k "fine slots", many more than there are elements (load about 0.1), so
+// nine elements in ten are alone in their slot and their local rank is simply the number of elements
+// in lower slots: a prefix sum over the slot counters.  Elements sharing a slot are written to a
+// rank-indexed buffer and ordered by direct comparison of (key, pixel index).  The counters are W-bit
+// fields packed in 32-bit words (one shared-memory atomic per element returns the arrival ticket);
+// W = 4 first, and if a field overflows (16 or more elements in one slot: exact ties) the block starts
+// over with W = 8; 256 or more raises the segment's fallback flag.
+constexpr int kCntWords = 4096;          // 16 KB of packed counters: 32768 4-bit or 16384 8-bit fine slots
+constexpr int kColMax = 2048;            // dense list of the elements that share a fine slot
 struct LocalShared {
-    u64 buf[kBTile];
-    u32 slot[kBTile];
-    u32 tab[kTabBins + 4];
-    u32 fgbits[kBTile / 32];
+    u64 buf[kBTile];                     // elements sharing a fine slot, at [first rank of the slot + ticket]
+    u32 cntw[kCntWords];
+    u32 wpre[kCntWords];                 // elements in lower words
+    u32 fgbits[kBTile / 32];             // bit r: the element of local rank r is foreground
     u32 fgpre[kBTile / 32];
-    u32 woff[kBWarps];
+    u32 col[kColMax];                    // elements sharing a fine slot: {first rank:0..12, ticket:13..20, count:21..28} -> rank
+    u32 ncol;
     u32 scan_tmp[kBWarps];
+    u32 woff[kBWarps];
     u64 red64[kBWarps];
-    u32 redchain[kBWarps];
     long long red[kBWarps];
-    u32 chain;
     u32 skip;
     u64 base;
 };
-constexpr u32 kSlotFirst = 1u << 29;    // payload bit: first element (in arrival order) of its slot
+
+template <int W>
+__device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields of w
+    if (W == 8) return __dp4a(w, 0x01010101u, 0u);
+    return __dp4a(w & 0x0f0f0f0fu, 0x01010101u, 0u) + __dp4a((w >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u);
+}
+
+// One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
+// rk[j] ends as the local rank of element j * kBThreads + tid.
+template <int W>
+__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restrict__ src, const u32 *__restrict__ tab,
+                                            u32 cnt, u32 xmax, const u32 (&keyA)[kBItems], u32 (&rk)[kBItems]) {
+    constexpr u32 FW = 32 / W;                       // fields per word
+    constexpr u32 FM = (1u << W) - 1u;               // largest field value
+    constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 i = tid; i < (u32)kCntWords; i += kBThreads) sm.cntw[i] = 0;
+    if (tid < kBTile / 32) sm.fgbits[tid] = 0;
+    if (tid == 0) sm.ncol = 0;
+    __syncthreads();
+
+    // phase A: one atomic per element; {fine slot:0..14, ticket:16..23}
+    bool over = false;
+#pragma unroll
+    for (int j = 0; j < kBItems; ++j) {
+        const u32 idx = j * kBThreads + tid;
+        rk[j] = 0;
+        if (j * kBThreads >= cnt) continue;          // block-uniform: the bucket is smaller than its capacity
+        if (idx < cnt) {
+            // the keys of one bucket share a few table entries: the loads broadcast out of L1
+            const u32 f = (cdf_pos(keyA[j], tab, xmax) & 0xffffu) >> FSHIFT;
+            const u32 sh = (f % FW) * W;
+            const u32 t = (atomicAdd(&sm.cntw[f / FW], 1u << sh) >> sh) & FM;
+            over |= t == FM;                         // the field was already full: this add spilled into the next one
+            rk[j] = f | (t << 16);
+        }
+    }
+    if (__syncthreads_or(over)) return false;
+
+    // exclusive scan of the word sums: warp w owns words [256 w, 256 w + 256), 4 consecutive per lane
+    {
+        constexpr int kChunk = kCntWords / kBWarps;
+        const uint4 *c4p = reinterpret_cast<const uint4 *>(sm.cntw + warp * kChunk);
+        uint4 *o4p = reinterpret_cast<uint4 *>(sm.wpre + warp * kChunk);
+        u32 running = 0;
+#pragma unroll
+        for (int r = 0; r < kChunk / 128; ++r) {
+            const uint4 c4 = c4p[r * 32 + lane];
+            const u32 sx = field_sum<W>(c4.x), sy = field_sum<W>(c4.y), sz = field_sum<W>(c4.z), sw = field_sum<W>(c4.w);
+            const u32 tot = sx + sy + sz + sw;
+            u32 incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(RTDA_FULL_MASK, incl, o);
+                if (lane >= (u32)o) incl += t;
+            }
+            uint4 o4;
+            o4.x = running + incl - tot;
+            o4.y = o4.x + sx;
+            o4.z = o4.y + sy;
+            o4.w = o4.z + sz;
+            o4p[r * 32 + lane] = o4;
+            running += __shfl_sync(RTDA_FULL_MASK, incl, 31);
+        }
+        if (lane == 0) sm.woff[warp] = running;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < kBWarps; ++w) {
+            const u32 t = sm.woff[w];
+            sm.woff[w] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+
+    // phase B: rank of the elements that are alone in their slot; the others go to the buffer.
+    // rk[j] becomes {first rank of the slot:0..12, ticket:13..20, elements in the slot:21..28}
+#pragma unroll
+    for (int j = 0; j < kBItems; ++j) {
+        const u32 idx = j * kBThreads + tid;
+        if (j * kBThreads >= cnt) break;
+        if (idx < cnt) {
+            const u32 f = rk[j] & 0xffffu, t = rk[j] >> 16;
+            const u32 wi = f / FW, sh = (f % FW) * W;
+            const u32 word = sm.cntw[wi];
+            const u32 c = (word >> sh) & FM;
+            const u32 first = sm.wpre[wi] + sm.woff[wi / (kCntWords / kBWarps)] + field_sum<W>(word & ((1u << sh) - 1u));
+            rk[j] = first | (t << 13) | (c << 21);
+            if (c == 1) {
+                if (reinterpret_cast<const u32 *>(src + idx)[0] & kPayloadFg) atomicOr(&sm.fgbits[first >> 5], 1u << (first & 31u));
+            } else {
+                sm.buf[first + t] = src[idx];
+                const u32 q = atomicAdd(&sm.ncol, 1u);          // dense list: phase C runs without idle lanes
+                if (q < (u32)kColMax) { sm.col[q] = rk[j]; rk[j] = 0x80000000u | q; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase C: elements sharing a slot are ordered by (key, pixel index)
+    const u64 cmp_mask = ~((u64)(kPayloadFg | kPayloadNeg));
+    const u32 ncol = sm.ncol < (u32)kColMax ? sm.ncol : (u32)kColMax;
+    for (u32 i = tid; i < ncol; i += kBThreads) {
+        const u32 d = sm.col[i];
+        const u32 first = d & 0x1fffu, c = d >> 21;
+        const u64 e = sm.buf[first + ((d >> 13) & 0xffu)];
+        const u64 ce = e & cmp_mask;
+        u32 pred = 0;
+        for (u32 m = 0; m < c; ++m) pred += ((sm.buf[first + m] & cmp_mask) < ce) ? 1u : 0u;
+        const u32 r = first + pred;
+        if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
+        sm.col[i] = r;
+    }
+    if (sm.ncol > (u32)kColMax) {                     // list full (heavy ties): the rest in place, lanes idle
+#pragma unroll
+        for (int j = 0; j < kBItems; ++j) {
+            if (j * kBThreads >= cnt) break;
+            const u32 c = rk[j] >> 21;
+            if (!(rk[j] & 0x80000000u) && c > 1) {
+                const u32 first = rk[j] & 0x1fffu;
+                const u64 e = sm.buf[first + ((rk[j] >> 13) & 0xffu)];
+                const u64 ce = e & cmp_mask;
+                u32 pred = 0;
+                for (u32 m = 0; m < c; ++m) pred += ((sm.buf[first + m] & cmp_mask) < ce) ? 1u : 0u;
+                const u32 r = first + pred;
+                if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
+                rk[j] = r;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kBItems; ++j) {
+        if (j * kBThreads >= cnt) break;
+        rk[j] = (rk[j] & 0x80000000u) ? sm.col[rk[j] & 0x7fffffffu] : (rk[j] & 0x1fffu);
+    }
+    __syncthreads();
+    return true;
+}
 
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
@@ -381,12 +557,13 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     }
     const u64 *src = regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile;
     const u32 xmax = (nb[seg] << 16) - 1u;
-    // the keys of phase A are requested first: the setup below runs while they travel
+    // the keys are requested first: the setup below runs while they travel
     u32 keyA[kBItems];
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
         const u32 idx = j * kBThreads + tid;
         keyA[j] = 0;
+        if (j * kBThreads >= cnt) break;
         if (idx < cnt) keyA[j] = reinterpret_cast<const u32 *>(src + idx)[1];
     }
 
@@ -396,12 +573,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc64 += __shfl_xor_sync(RTDA_FULL_MASK, acc64, o);
     if (lane == 0) sm.red64[warp] = acc64;
-    {
-        const u32 *tsrc = table + (size_t)seg * (kTabBins + 1);
-        for (u32 k = tid; k < (u32)kTabBins + 1u; k += kBThreads) sm.tab[k] = tsrc[k];
-    }
-    for (u32 i = tid; i < ((cnt + 127u) & ~127u); i += kBThreads) sm.slot[i] = 0;   // whole uint4 groups of the scan
-    if (tid < kBTile / 32) sm.fgbits[tid] = 0;
+    const u32 *tab = table + (size_t)seg * (kTabBins + 1);
     __syncthreads();
     if (tid == 0) {
         u64 t = 0;
@@ -410,88 +582,14 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         sm.base = t;
     }
 
-    // phase A: slot = fractional position inside the bucket x count; the ticket is the element's
-    // arrival order inside its slot.  {slot:0..12, ticket:16..28} per element stay in registers.
-    u32 stt[kBItems];
-#pragma unroll
-    for (int j = 0; j < kBItems; ++j) {
-        const u32 idx = j * kBThreads + tid;
-        stt[j] = 0;
-        if (idx < cnt) {
-            const u32 x = cdf_pos(keyA[j], sm.tab, xmax);
-            const u32 s = ((x & 0xffffu) * cnt) >> 16;
-            stt[j] = s | (atomicAdd(&sm.slot[s], 1u) << 16);
+    u32 rk[kBItems];
+    if (!local_ranks<4>(sm, src, tab, cnt, xmax, keyA, rk)) {
+        if (!local_ranks<8>(sm, src, tab, cnt, xmax, keyA, rk)) {   // 256 or more exact ties: the LSD path redoes the segment
+            if (tid == 0) { fb_flag[seg] = 1u; *fb_any = 1u; }
+            return;
         }
     }
-    __syncthreads();
     const u32 base_cnt = (u32)sm.base, base_fg = (u32)(sm.base >> 32);
-
-    // exclusive scan of the slot counts: warp w owns slots [512 w, 512 w + 512), 4 consecutive per lane
-    {
-        constexpr int kChunk = kBTile / kBWarps;
-        uint4 *sl4 = reinterpret_cast<uint4 *>(sm.slot + warp * kChunk);
-        u32 running = 0, maxc = 0;
-#pragma unroll
-        for (int r = 0; r < kChunk / 128; ++r) {
-            if (warp * kChunk + r * 128 >= cnt) break;           // slots >= cnt are never used (warp-uniform)
-            uint4 c4 = sl4[r * 32 + lane];
-            const u32 m01 = c4.x > c4.y ? c4.x : c4.y, m23 = c4.z > c4.w ? c4.z : c4.w;
-            maxc = maxc > m01 ? maxc : m01;
-            maxc = maxc > m23 ? maxc : m23;
-            const u32 tot = c4.x + c4.y + c4.z + c4.w;
-            u32 incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const u32 t = __shfl_up_sync(RTDA_FULL_MASK, incl, o);
-                if (lane >= (u32)o) incl += t;
-            }
-            u32 e = running + incl - tot;
-            uint4 o4;
-            o4.x = e; e += c4.x;
-            o4.y = e; e += c4.y;
-            o4.z = e; e += c4.z;
-            o4.w = e;
-            sl4[r * 32 + lane] = o4;
-            running += __shfl_sync(RTDA_FULL_MASK, incl, 31);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const u32 t = __shfl_xor_sync(RTDA_FULL_MASK, maxc, o);
-            maxc = t > maxc ? t : maxc;
-        }
-        if (lane == 0) { sm.woff[warp] = running; sm.redchain[warp] = maxc; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        u32 run = 0, mc = 0;
-#pragma unroll
-        for (int w = 0; w < kBWarps; ++w) {
-            const u32 t = sm.woff[w];
-            sm.woff[w] = run;
-            run += t;
-            mc = sm.redchain[w] > mc ? sm.redchain[w] : mc;
-        }
-        sm.chain = mc;
-    }
-    __syncthreads();
-    if (sm.chain > (u32)kChainMax) {               // massive ties: quadratic chain work, let the LSD path do it
-        if (tid == 0) { fb_flag[seg] = 1u; *fb_any = 1u; }
-        return;
-    }
-
-    // phase B: placement in slot order; foreground bitmap by position; bit 29 marks a slot's first element
-#pragma unroll
-    for (int j = 0; j < kBItems; ++j) {
-        const u32 idx = j * kBThreads + tid;
-        if (idx < cnt) {
-            const u64 v = src[idx];
-            const u32 s = stt[j] & 0xffffu, t = stt[j] >> 16;
-            const u32 pos = sm.slot[s] + sm.woff[s / (kBTile / kBWarps)] + t;
-            sm.buf[pos] = t ? v : (v | kSlotFirst);
-            if ((u32)v & kPayloadFg) atomicOr(&sm.fgbits[pos >> 5], 1u << (pos & 31u));
-        }
-    }
-    __syncthreads();
     {
         const u32 v = tid < kBTile / 32 ? (u32)__popc(sm.fgbits[tid]) : 0u;
         const u32 e = block_excl_scan<kBWarps, u32>(v, sm.scan_tmp, nullptr);
@@ -499,42 +597,26 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     }
     __syncthreads();
 
-    // phase C: order inside the slot by (key, pixel index), ranks, lovasz_grad, dot product, gradient
+    // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
     float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
-    const u64 cmp_mask = ~((u64)(kPayloadFg | kPayloadNeg | kSlotFirst));
     long long acc = 0;
-#pragma unroll 2
-    for (int k = 0; k < kBItems; ++k) {
-        const u32 q = k * kBThreads + tid;
-        if (q >= cnt) break;
-        const u64 e = sm.buf[q];
-        const u32 key = (u32)(e >> 32), pay = (u32)e;
-        const u64 ce = e & cmp_mask;
-        u32 pred = 0, fpred = 0;
-        u32 cs = q;
-        if (!(pay & kSlotFirst)) {
-            for (;;) {                              // elements of the same slot to the left, down to its first
-                const u64 x = sm.buf[--cs];
-                if ((x & cmp_mask) < ce) { ++pred; fpred += ((u32)x >> 31); }
-                if ((u32)x & kSlotFirst) break;
-            }
+#pragma unroll
+    for (int j = 0; j < kBItems; ++j) {
+        const u32 idx = j * kBThreads + tid;
+        if (j * kBThreads >= cnt) break;
+        if (idx < cnt) {
+            const u32 pay = reinterpret_cast<const u32 *>(src + idx)[0];
+            const u32 lr = rk[j];
+            const u32 r = base_cnt + lr;                                  // 0-based rank in the sorted segment
+            const u32 f_ex = base_fg + sm.fgpre[lr >> 5] + (u32)__popc(sm.fgbits[lr >> 5] & ((1u << (lr & 31u)) - 1u));
+            const u32 f_in = f_ex + (pay >> 31);
+            const float jac = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_in), __uint2float_rn(G + r + 1u - f_in)));
+            const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
+            const float gr = __fsub_rn(jac, jprev);
+            const float err = __uint_as_float(~keyA[j]);
+            acc += loss_term_fix(err, gr);
+            if (ug) ug[pay & kPayloadIdx] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
         }
-        for (u32 j = q + 1; j < cnt; ++j) {        // and to the right, up to the next slot's first
-            const u64 x = sm.buf[j];
-            if ((u32)x & kSlotFirst) break;
-            if ((x & cmp_mask) < ce) { ++pred; fpred += ((u32)x >> 31); }
-        }
-        const u32 fgq = pay >> 31;
-        const u32 r = base_cnt + cs + pred;                                  // 0-based rank in the sorted segment
-        const u32 f_ex = base_fg + sm.fgpre[cs >> 5] + (u32)__popc(sm.fgbits[cs >> 5] & ((1u << (cs & 31u)) - 1u)) + fpred;
-        const u32 f_in = f_ex + fgq;
-        // lovasz_loss.py:60-69, as in k_rank_last
-        const float jac = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_in), __uint2float_rn(G + r + 1u - f_in)));
-        const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
-        const float gr = __fsub_rn(jac, jprev);
-        const float err = __uint_as_float(~key);
-        acc += loss_term_fix(err, gr);
-        if (ug) ug[pay & (kSlotFirst - 1u)] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(RTDA_FULL_MASK, acc, o);

@@ -94,6 +94,11 @@ def main():
             occ = cur & 0xffffffff
             nbs = ws[int(o[17]):int(o[17]) + 4 * S].view(torch.int32).cpu().numpy()
             print(f"    buckets per segment {nbs.tolist()}")
+            for sgi in (0, 7):
+                o_ = occ[sgi, :nbs[sgi]]
+                top = np.argsort(-o_)[:6]
+                print(f"    seg {sgi}: largest buckets {[(int(i), int(o_[i])) for i in top]}; first 4 {o_[:4].tolist()} last 4 {o_[-4:].tolist()}; "
+                      f"buckets > 1.25 x mean: {int((o_ > 1.25 * o_.mean()).sum())}, std/mean {o_.std() / o_.mean():.3f}")
             print(f"    bucket occupancy: max {occ.max()}, mean of non-empty {occ[occ > 0].mean():.0f}, "
                   f"p99 {np.percentile(occ[occ > 0], 99):.0f}, min non-empty {occ[occ > 0].min()}")
         print(f"c2 {path}: {dt * 1e3:.3f} ms/step wall (with profiling events), lsd-segments {int(fb.sum())}")

@@ -15,6 +15,13 @@ from rtda_semanticsegmentation_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["bucket", "lsd"])
+def sort_path(request):
+    rtda.set_sort_path(request.param)
+    yield request.param
+    rtda.set_sort_path("bucket")
+
+
 def reference_step(logits, labels, weight, per_image, go=1.0):
     lg = logits.clone().requires_grad_(True)
     ce = torch.nn.CrossEntropyLoss(ignore_index=255)(lg, labels)                 # train_lovasz.py:98

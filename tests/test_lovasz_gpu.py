@@ -19,6 +19,15 @@ pytestmark = pytest.mark.gpu
 LOSS_RTOL = 2e-6
 
 
+@pytest.fixture(autouse=True, params=["bucket", "lsd"])
+def sort_path(request):
+    """Every test of this module runs with both sort paths of the forward: the sample-partitioned
+    bucket sort (default; falls back per segment on the device) and the LSD radix sort."""
+    rtda.set_sort_path(request.param)
+    yield request.param
+    rtda.set_sort_path("bucket")
+
+
 def run_cuda(probas, labels, ignore=255, per_image=False, grad_out=None, label_dtype=None, module=True):
     p = torch.as_tensor(probas).cuda().requires_grad_(True)
     l = torch.as_tensor(labels).cuda()
@@ -261,3 +270,43 @@ def test_hypothesis_invariants():
                 assert np.abs(grad.astype(np.float64)).sum() == pytest.approx(want, abs=1e-4)
 
     run()
+
+
+def test_bucket_path_is_taken_and_falls_back_only_on_ties(sort_path):
+    """Which path sorted each (group, class) segment: the bucket path for softmax-like errors of
+    every size, the LSD radix path (device-side fallback, no host involvement) for massive exact
+    ties - and bit-exact results either way (checked by assert_matches_oracle)."""
+    if sort_path != "bucket":
+        pytest.skip("path report of the default mode")
+    for (b, h, w, per_image) in [(1, 16, 24, False), (2, 128, 256, False), (2, 128, 256, True), (1, 512, 512, False)]:
+        probas, labels = synthetic.confident_case(b, h, w, seed=31)
+        assert_matches_oracle(probas.numpy(), labels.numpy(), 255, per_image, tag="conf")
+        assert int(rtda.segment_sort_paths((b, 19, h, w), per_image).sum()) == 0, (b, h, w, per_image)
+    probas, labels = synthetic.diffuse_case(2, 256, 256, seed=32)
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="diffuse")
+    assert int(rtda.segment_sort_paths((2, 19, 256, 256), False).sum()) == 0
+    g = torch.Generator().manual_seed(33)
+    labels = torch.randint(0, 5, (2, 100, 100), generator=g)
+    uniform = torch.full((2, 5, 100, 100), 0.2)                          # 2 distinct keys per class: thousands of ties
+    assert_matches_oracle(uniform.numpy(), labels.numpy(), tag="uniform")
+    assert int(rtda.segment_sort_paths((2, 5, 100, 100), False).sum()) == 5
+    # a few hundred ties inside otherwise smooth data stay on the bucket path (8-bit slot counters)
+    probas, labels = synthetic.confident_case(1, 256, 256, seed=34)
+    probas[:, :, :2, :100] = probas[:, :, :1, :1]                          # 200 pixels share one probability vector
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="200 ties")
+    assert int(rtda.segment_sort_paths((1, 19, 256, 256), False).sum()) == 0
+
+
+def test_mixed_segments_some_fall_back(sort_path):
+    """One class with massive ties (its probability is constant), the others smooth: only that
+    segment is redone by the LSD path; all of them agree with the oracle bit for bit."""
+    g = torch.Generator().manual_seed(35)
+    logits = torch.randn((2, 6, 96, 96), generator=g) * 2
+    probas = torch.softmax(logits, 1)
+    probas[:, 3] = 0.125                                                   # class 3: two distinct error values
+    labels = torch.randint(0, 6, (2, 96, 96), generator=g)
+    labels[torch.rand((2, 96, 96), generator=g) < 0.1] = 255
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="mixed")
+    if sort_path == "bucket":
+        fb = rtda.segment_sort_paths((2, 6, 96, 96), False).cpu().numpy().ravel()
+        assert fb[3] == 1 and fb.sum() == 1, fb
