@@ -367,31 +367,55 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 // k_local: level 2.  One block per (segment, bucket), segment-major so that the 4-byte gradient
 // scatter of one segment stays inside one L2-resident plane.
 //
+// The bucket (at most 64 KB, contiguous) is brought into shared memory by ONE bulk asynchronous copy
+// (cp.async.bulk, the 1-D TMA path) signalled on an mbarrier; every later access to an element is a
+// shared-memory load.
+//
 // The fractional part of an element's cumulative position is its place inside the bucket.  Its top
-// bits select one of kFine / 2^k "fine slots", many more than there are elements (load about 0.1), so
-// nine elements in ten are alone in their slot and their local rank is simply the number of elements
-// in lower slots: a prefix sum over the slot counters.  Elements sharing a slot are written to a
-// rank-indexed buffer and ordered by direct comparison of (key, pixel index).  The counters are W-bit
-// fields packed in 32-bit words (one shared-memory atomic per element returns the arrival ticket);
-// W = 4 first, and if a field overflows (16 or more elements in one slot: exact ties) the block starts
-// over with W = 8; 256 or more raises the segment's fallback flag.
+// bits select one of 32768 "fine slots", many more than there are elements (load 0.1 - 0.2), so
+// most elements are alone in their slot and their local rank is simply the number of elements
+// in lower slots: a prefix sum over the slot counters.  Elements sharing a slot are ordered by
+// direct comparison of (key, pixel index).  The counters are W-bit fields packed in 32-bit words
+// (one shared-memory atomic per element returns the arrival ticket); W = 4 first, and if a field
+// overflows (16 or more elements in one slot: exact ties) the block starts over with W = 8 (16384
+// slots); 256 or more raises the segment's fallback flag.
 constexpr int kCntWords = 4096;          // 16 KB of packed counters: 32768 4-bit or 16384 8-bit fine slots
-constexpr int kColMax = 2048;            // dense list of the elements that share a fine slot
+constexpr int kColMax = 1024;            // dense list of the elements that share a fine slot
 struct LocalShared {
-    u64 buf[kBTile];                     // elements sharing a fine slot, at [first rank of the slot + ticket]
+    u64 stage[kBTile];                   // the bucket, in the order k_part wrote it
     u32 cntw[kCntWords];
-    u32 wpre[kCntWords];                 // elements in lower words
+    unsigned short wpre[kCntWords];      // elements in lower words of the same warp chunk
+    unsigned short where[kBTile];        // [first rank of a shared slot + ticket] -> index into stage
+    u32 col[kColMax];                    // elements sharing a slot: {first rank:0..12, ticket:13..20, count:21..28} -> rank
     u32 fgbits[kBTile / 32];             // bit r: the element of local rank r is foreground
     u32 fgpre[kBTile / 32];
-    u32 col[kColMax];                    // elements sharing a fine slot: {first rank:0..12, ticket:13..20, count:21..28} -> rank
-    u32 ncol;
     u32 scan_tmp[kBWarps];
     u32 woff[kBWarps];
     u64 red64[kBWarps];
     long long red[kBWarps];
-    u32 skip;
+    u64 mbar;
     u64 base;
+    u32 ncol;
+    u32 skip;
 };
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 template <int W>
 __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields of w
@@ -402,16 +426,12 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 // One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
 // rk[j] ends as the local rank of element j * kBThreads + tid.
 template <int W>
-__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restrict__ src, const u32 *__restrict__ tab,
-                                            u32 cnt, u32 xmax, const u32 (&keyA)[kBItems], u32 (&rk)[kBItems]) {
+__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, u32 cnt, u32 xmax,
+                                            u32 (&rk)[kBItems]) {
     constexpr u32 FW = 32 / W;                       // fields per word
     constexpr u32 FM = (1u << W) - 1u;               // largest field value
     constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (u32 i = tid; i < (u32)kCntWords; i += kBThreads) sm.cntw[i] = 0;
-    if (tid < kBTile / 32) sm.fgbits[tid] = 0;
-    if (tid == 0) sm.ncol = 0;
-    __syncthreads();
 
     // phase A: one atomic per element; {fine slot:0..14, ticket:16..23}
     bool over = false;
@@ -422,7 +442,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
         if (j * kBThreads >= cnt) continue;          // block-uniform: the bucket is smaller than its capacity
         if (idx < cnt) {
             // the keys of one bucket share a few table entries: the loads broadcast out of L1
-            const u32 f = (cdf_pos(keyA[j], tab, xmax) & 0xffffu) >> FSHIFT;
+            const u32 f = (cdf_pos((u32)(sm.stage[idx] >> 32), tab, xmax) & 0xffffu) >> FSHIFT;
             const u32 sh = (f % FW) * W;
             const u32 t = (atomicAdd(&sm.cntw[f / FW], 1u << sh) >> sh) & FM;
             over |= t == FM;                         // the field was already full: this add spilled into the next one
@@ -431,11 +451,11 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
     }
     if (__syncthreads_or(over)) return false;
 
-    // exclusive scan of the word sums: warp w owns words [256 w, 256 w + 256), 4 consecutive per lane
+    // exclusive scan of the word sums inside each warp's chunk of 256 words (4 consecutive per lane)
     {
         constexpr int kChunk = kCntWords / kBWarps;
         const uint4 *c4p = reinterpret_cast<const uint4 *>(sm.cntw + warp * kChunk);
-        uint4 *o4p = reinterpret_cast<uint4 *>(sm.wpre + warp * kChunk);
+        uint2 *o2p = reinterpret_cast<uint2 *>(sm.wpre + warp * kChunk);
         u32 running = 0;
 #pragma unroll
         for (int r = 0; r < kChunk / 128; ++r) {
@@ -448,30 +468,27 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
                 const u32 t = __shfl_up_sync(RTDA_FULL_MASK, incl, o);
                 if (lane >= (u32)o) incl += t;
             }
-            uint4 o4;
-            o4.x = running + incl - tot;
-            o4.y = o4.x + sx;
-            o4.z = o4.y + sy;
-            o4.w = o4.z + sz;
-            o4p[r * 32 + lane] = o4;
+            const u32 e0 = running + incl - tot, e1 = e0 + sx, e2 = e1 + sy, e3 = e2 + sz;
+            o2p[r * 32 + lane] = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
             running += __shfl_sync(RTDA_FULL_MASK, incl, 31);
         }
         if (lane == 0) sm.woff[warp] = running;
     }
     __syncthreads();
-    if (tid == 0) {
-        u32 run = 0;
+    if (warp == 0) {                                 // exclusive scan of the 16 chunk totals
+        const u32 v = lane < (u32)kBWarps ? sm.woff[lane] : 0u;
+        u32 incl = v;
 #pragma unroll
-        for (int w = 0; w < kBWarps; ++w) {
-            const u32 t = sm.woff[w];
-            sm.woff[w] = run;
-            run += t;
+        for (int o = 1; o < kBWarps; o <<= 1) {
+            const u32 t = __shfl_up_sync(RTDA_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += t;
         }
+        if (lane < (u32)kBWarps) sm.woff[lane] = incl - v;
     }
     __syncthreads();
 
-    // phase B: rank of the elements that are alone in their slot; the others go to the buffer.
-    // rk[j] becomes {first rank of the slot:0..12, ticket:13..20, elements in the slot:21..28}
+    // phase B: rank of the elements that are alone in their slot; the others register in `where`
+    // and in the dense list.  rk[j] becomes {first rank of the slot:0..12, ticket:13..20, count:21..28}
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
         const u32 idx = j * kBThreads + tid;
@@ -481,12 +498,12 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
             const u32 wi = f / FW, sh = (f % FW) * W;
             const u32 word = sm.cntw[wi];
             const u32 c = (word >> sh) & FM;
-            const u32 first = sm.wpre[wi] + sm.woff[wi / (kCntWords / kBWarps)] + field_sum<W>(word & ((1u << sh) - 1u));
+            const u32 first = (u32)sm.wpre[wi] + sm.woff[wi / (kCntWords / kBWarps)] + field_sum<W>(word & ((1u << sh) - 1u));
             rk[j] = first | (t << 13) | (c << 21);
             if (c == 1) {
-                if (reinterpret_cast<const u32 *>(src + idx)[0] & kPayloadFg) atomicOr(&sm.fgbits[first >> 5], 1u << (first & 31u));
+                if ((u32)sm.stage[idx] & kPayloadFg) atomicOr(&sm.fgbits[first >> 5], 1u << (first & 31u));
             } else {
-                sm.buf[first + t] = src[idx];
+                sm.where[first + t] = (unsigned short)idx;
                 const u32 q = atomicAdd(&sm.ncol, 1u);          // dense list: phase C runs without idle lanes
                 if (q < (u32)kColMax) { sm.col[q] = rk[j]; rk[j] = 0x80000000u | q; }
             }
@@ -496,29 +513,30 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
 
     // phase C: elements sharing a slot are ordered by (key, pixel index)
     const u64 cmp_mask = ~((u64)(kPayloadFg | kPayloadNeg));
-    const u32 ncol = sm.ncol < (u32)kColMax ? sm.ncol : (u32)kColMax;
+    const u32 ncol_all = sm.ncol;
+    const u32 ncol = ncol_all < (u32)kColMax ? ncol_all : (u32)kColMax;
     for (u32 i = tid; i < ncol; i += kBThreads) {
         const u32 d = sm.col[i];
         const u32 first = d & 0x1fffu, c = d >> 21;
-        const u64 e = sm.buf[first + ((d >> 13) & 0xffu)];
+        const u64 e = sm.stage[sm.where[first + ((d >> 13) & 0xffu)]];
         const u64 ce = e & cmp_mask;
         u32 pred = 0;
-        for (u32 m = 0; m < c; ++m) pred += ((sm.buf[first + m] & cmp_mask) < ce) ? 1u : 0u;
+        for (u32 m = 0; m < c; ++m) pred += ((sm.stage[sm.where[first + m]] & cmp_mask) < ce) ? 1u : 0u;
         const u32 r = first + pred;
         if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
         sm.col[i] = r;
     }
-    if (sm.ncol > (u32)kColMax) {                     // list full (heavy ties): the rest in place, lanes idle
+    if (ncol_all > (u32)kColMax) {                    // list full (heavy ties): the rest in place, lanes idle
 #pragma unroll
         for (int j = 0; j < kBItems; ++j) {
             if (j * kBThreads >= cnt) break;
-            const u32 c = rk[j] >> 21;
+            const u32 c = (rk[j] >> 21) & 0xffu;
             if (!(rk[j] & 0x80000000u) && c > 1) {
                 const u32 first = rk[j] & 0x1fffu;
-                const u64 e = sm.buf[first + ((rk[j] >> 13) & 0xffu)];
+                const u64 e = sm.stage[j * kBThreads + tid];
                 const u64 ce = e & cmp_mask;
                 u32 pred = 0;
-                for (u32 m = 0; m < c; ++m) pred += ((sm.buf[first + m] & cmp_mask) < ce) ? 1u : 0u;
+                for (u32 m = 0; m < c; ++m) pred += ((sm.stage[sm.where[first + m]] & cmp_mask) < ce) ? 1u : 0u;
                 const u32 r = first + pred;
                 if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
                 rk[j] = r;
@@ -531,21 +549,29 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u64 *__restri
         if (j * kBThreads >= cnt) break;
         rk[j] = (rk[j] & 0x80000000u) ? sm.col[rk[j] & 0x7fffffffu] : (rk[j] & 0x1fffu);
     }
-    __syncthreads();
     return true;
+}
+
+__device__ __forceinline__ void local_reset(LocalShared &sm) {
+    for (u32 i = threadIdx.x; i < (u32)kCntWords; i += kBThreads) sm.cntw[i] = 0;
+    if (threadIdx.x < kBTile / 32) sm.fgbits[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sm.ncol = 0;
 }
 
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u64 *__restrict__ cursor, u32 *__restrict__ fb_flag,
         u32 *__restrict__ fb_any, long long *__restrict__ partial_b, float *__restrict__ unit_grad) {
-    extern __shared__ __align__(16) unsigned char local_smem[];
+    extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 seg = blockIdx.x / (u32)geo.NBK;
     const u32 b = blockIdx.x - seg * (u32)geo.NBK;
     const u32 G = seg_fg[seg];
-    if (tid == 0) sm.skip = (G == 0 || ld_relaxed(fb_flag + seg) != 0 || b >= nb[seg]) ? 1u : 0u;
+    if (tid == 0) {
+        sm.skip = (G == 0 || ld_relaxed(fb_flag + seg) != 0 || b >= nb[seg]) ? 1u : 0u;
+        mbar_init(&sm.mbar, 1);
+    }
     __syncthreads();
     if (sm.skip) return;
     const u64 *cur = cursor + (size_t)seg * geo.NBK;
@@ -555,25 +581,18 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         if (tid == 0) partial_b[(size_t)seg * geo.NBK + b] = 0;
         return;
     }
-    const u64 *src = regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile;
+    // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
+    if (tid == 0) bulk_load(sm.stage, regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile, ((cnt + 1u) & ~1u) * 8u, &sm.mbar);
     const u32 xmax = (nb[seg] << 16) - 1u;
-    // the keys are requested first: the setup below runs while they travel
-    u32 keyA[kBItems];
-#pragma unroll
-    for (int j = 0; j < kBItems; ++j) {
-        const u32 idx = j * kBThreads + tid;
-        keyA[j] = 0;
-        if (j * kBThreads >= cnt) break;
-        if (idx < cnt) keyA[j] = reinterpret_cast<const u32 *>(src + idx)[1];
-    }
+    const u32 *tab = table + (size_t)seg * (kTabBins + 1);
 
-    // elements (low word) and foreground elements (high word) of the earlier buckets
+    // meanwhile: elements (low word) and foreground elements (high word) of the earlier buckets
     u64 acc64 = 0;
     for (u32 i = tid; i < b; i += kBThreads) acc64 += cur[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc64 += __shfl_xor_sync(RTDA_FULL_MASK, acc64, o);
     if (lane == 0) sm.red64[warp] = acc64;
-    const u32 *tab = table + (size_t)seg * (kTabBins + 1);
+    local_reset(sm);
     __syncthreads();
     if (tid == 0) {
         u64 t = 0;
@@ -581,10 +600,13 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         for (int w = 0; w < kBWarps; ++w) t += sm.red64[w];
         sm.base = t;
     }
+    mbar_wait(&sm.mbar, 0);
 
     u32 rk[kBItems];
-    if (!local_ranks<4>(sm, src, tab, cnt, xmax, keyA, rk)) {
-        if (!local_ranks<8>(sm, src, tab, cnt, xmax, keyA, rk)) {   // 256 or more exact ties: the LSD path redoes the segment
+    if (!local_ranks<4>(sm, tab, cnt, xmax, rk)) {
+        local_reset(sm);
+        __syncthreads();
+        if (!local_ranks<8>(sm, tab, cnt, xmax, rk)) {   // 256 or more exact ties: the LSD path redoes the segment
             if (tid == 0) { fb_flag[seg] = 1u; *fb_any = 1u; }
             return;
         }
@@ -605,7 +627,8 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         const u32 idx = j * kBThreads + tid;
         if (j * kBThreads >= cnt) break;
         if (idx < cnt) {
-            const u32 pay = reinterpret_cast<const u32 *>(src + idx)[0];
+            const u64 e = sm.stage[idx];
+            const u32 pay = (u32)e;
             const u32 lr = rk[j];
             const u32 r = base_cnt + lr;                                  // 0-based rank in the sorted segment
             const u32 f_ex = base_fg + sm.fgpre[lr >> 5] + (u32)__popc(sm.fgbits[lr >> 5] & ((1u << (lr & 31u)) - 1u));
@@ -613,7 +636,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const float jac = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_in), __uint2float_rn(G + r + 1u - f_in)));
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
             const float gr = __fsub_rn(jac, jprev);
-            const float err = __uint_as_float(~keyA[j]);
+            const float err = __uint_as_float(~(u32)(e >> 32));
             acc += loss_term_fix(err, gr);
             if (ug) ug[pay & kPayloadIdx] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
         }
