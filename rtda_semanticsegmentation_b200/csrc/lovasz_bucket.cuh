@@ -561,7 +561,7 @@ __device__ __forceinline__ void local_reset(LocalShared &sm) {
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u64 *__restrict__ cursor, u32 *__restrict__ fb_flag,
-        u32 *__restrict__ fb_any, long long *__restrict__ partial_b, float *__restrict__ unit_grad) {
+        u32 *__restrict__ fb_any, unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad) {
     extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -577,10 +577,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     const u64 *cur = cursor + (size_t)seg * geo.NBK;
     const u32 cnt = (u32)cur[b];
     if (cnt > (u32)kBTile) return;                 // overflowed in k_part (flag already raised)
-    if (cnt == 0) {
-        if (tid == 0) partial_b[(size_t)seg * geo.NBK + b] = 0;
-        return;
-    }
+    if (cnt == 0) return;
     // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
     if (tid == 0) bulk_load(sm.stage, regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile, ((cnt + 1u) & ~1u) * 8u, &sm.mbar);
     const u32 xmax = (nb[seg] << 16) - 1u;
@@ -649,6 +646,6 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         long long t = 0;
 #pragma unroll
         for (int w = 0; w < kBWarps; ++w) t += sm.red[w];
-        partial_b[(size_t)seg * geo.NBK + b] = t;
+        atomicAdd(&seg_sum[seg], (unsigned long long)t);            // integer: the order of the adds does not matter
     }
 }
