@@ -8,6 +8,7 @@ from . import _lib
 from .hybrid_loss import HybridCELovasz, hybrid_ce_lovasz
 from .lovasz_loss import (LovaszSoftmax, flatten_probas, isnan, lovasz_grad, lovasz_softmax,
                           lovasz_softmax_flat, mean, segment_sort_paths, set_sort_path)
+from .step_metrics import StepMetrics
 from .metrics import (ConfusionMatrix, confusion_matrix, confusion_matrix_from_logits, fast_hist,
                       mean_iou, per_class_iou)
 
@@ -15,7 +16,7 @@ __all__ = [
     "LovaszSoftmax", "lovasz_softmax", "lovasz_softmax_flat", "lovasz_grad", "flatten_probas", "mean", "isnan",
     "fast_hist", "per_class_iou", "mean_iou", "confusion_matrix", "confusion_matrix_from_logits",
     "ConfusionMatrix", "HybridCELovasz", "hybrid_ce_lovasz", "build", "native_library_path",
-    "set_sort_path", "segment_sort_paths",
+    "set_sort_path", "segment_sort_paths", "StepMetrics",
 ]
 
 

@@ -77,3 +77,30 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_step_metrics_running_sums_and_periodic_read():
+    """StepMetrics: the reference's running sums / periodic logging values
+    (train_lovasz.py:133-158) without a per-step .item()."""
+    import torch
+    from rtda_semanticsegmentation_b200 import StepMetrics
+
+    m = StepMetrics(("loss_total", "loss_ce", "loss_lovasz"), "cpu", every=3)
+    want = {"loss_total": 0.0, "loss_ce": 0.0, "loss_lovasz": 0.0}
+    reads = []
+    for step in range(1, 8):
+        ce, lv = torch.tensor(0.1 * step), torch.tensor(0.01 * step, requires_grad=True)
+        tot = ce + 0.5 * lv
+        m.update(loss_total=tot, loss_ce=ce, loss_lovasz=lv)
+        for k, v in (("loss_total", tot), ("loss_ce", ce), ("loss_lovasz", lv)):
+            want[k] += float(v)
+        r = m.maybe_read(step)
+        if r is not None:
+            reads.append(step)
+            assert r["steps"] == step and abs(r["loss_ce"] - 0.1 * step) < 1e-7
+            assert abs(r["loss_total_sum"] - want["loss_total"]) < 1e-6
+    assert reads == [3, 6]
+    means = m.means()
+    assert abs(means["loss_lovasz"] - want["loss_lovasz"] / 7) < 1e-7
+    m.reset()
+    assert m.read()["loss_ce_sum"] == 0.0 and m.steps == 0
