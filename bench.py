@@ -399,7 +399,9 @@ def main():
     def step(p, l):
         p = p.detach().requires_grad_(True)
         if world > 1:
-            loss, _ = lovasz_softmax_sharded(p, l, ignore=255)
+            # fixed per-rank batch: the global image count is known, the all-reduce is asynchronous and
+            # the step's loss is this rank's share of the global mean (dist.lovasz_softmax_sharded)
+            loss, _ = lovasz_softmax_sharded(p, l, ignore=255, global_images=imgs * world)
         else:
             loss = crit(p, l)
         loss.backward()
@@ -417,9 +419,20 @@ def main():
     # ---- CUDA graphs of one fwd+bwd per input set (single GPU): the launch path of the timed region
     # is then free of host jitter.  Falls back to eager launches if capture is not possible.
     graphs = None
-    # single GPU only: capturing the NCCL all-reduce of the sharded path hung in round 1 (2 ranks),
-    # so N > 1 times eager launches
-    if world == 1 and not args.no_graph:
+    # N > 1: capturing the NCCL all-reduce itself hung (scripts/nccl_graph_probe.py), so the graph holds
+    # the LOCAL part of the sharded step - per-image loss of this rank's images times B_local/B_global,
+    # which is this rank's share of the global mean and has exactly the sharded gradient - and the one
+    # all-reduce of the packed partials is issued asynchronously after every replay (the same
+    # composition dist.lovasz_softmax_sharded(global_images=...) performs).
+    share = 1.0 / world
+    pending = [None]
+
+    def reduce_partials():
+        if pending[0] is not None:
+            pending[0].wait()                      # stream-side wait; at most one collective in flight
+        pending[0] = dist.all_reduce(lovasz.last_outputs.packed, op=dist.ReduceOp.SUM, async_op=True)
+
+    if not args.no_graph:
         try:
             graphs = []
             side = torch.cuda.Stream(dev)
@@ -428,14 +441,14 @@ def main():
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
                     for _ in range(2):
-                        crit(pin, l).backward()
+                        (crit(pin, l) * share).backward()
                         pin.grad = None
                 torch.cuda.current_stream(dev).wait_stream(side)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    gl = crit(pin, l)
+                    gl = crit(pin, l) * share if world > 1 else crit(pin, l)
                     gl.backward()
-                graphs.append((g, gl, pin))
+                graphs.append((g, gl, pin, lovasz.last_outputs))
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed, timing eager launches: {e!r}", file=sys.stderr)
@@ -452,7 +465,12 @@ def main():
     if graphs is not None:
         for i in range(args.steps):
             graphs[i % n_sets][0].replay()
+            if world > 1:
+                lovasz.last_outputs = graphs[i % n_sets][3]
+                reduce_partials()
         loss = graphs[(args.steps - 1) % n_sets][1]
+        if pending[0] is not None:
+            pending[0].wait()
     else:
         for i in range(args.steps):
             loss, grad = step(*sets[i % n_sets])
@@ -571,7 +589,7 @@ def main():
         "config": {
             "workload": f"{args.workload}: {desc}" + ("" if world == 1 else f"; per rank {imgs}x{C}x{H}x{W}, per_image=True sharded over {world} ranks, 1 all-reduce of 40 doubles"),
             "classes": C, "ignore": 255, "per_image": per_image, "distribution": "D_" + args.distribution,
-            "labels": "int64", "launch": "cuda_graph replay of the public fwd+bwd call (one graph per input set)" if graphs is not None else "eager",
+            "labels": "int64", "launch": ("cuda_graph replay of the public fwd+bwd call (one graph per input set)" + ("" if world == 1 else " on this rank's images, then one asynchronous all-reduce of the packed partials per step")) if graphs is not None else "eager",
             "l2_policy": f"{n_sets} distinct input sets ({n_sets * set_bytes >> 20} MiB > 126 MiB L2) rotated every step",
             "loss": loss_value, "sort_path": args.sort_path,
             "segments_sorted_by_lsd_fallback": int(rtda.segment_sort_paths((imgs, C, H, W), per_image).sum()),

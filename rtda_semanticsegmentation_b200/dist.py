@@ -75,15 +75,21 @@ def sharded_per_image_mean(group_loss, class_loss, class_present, group=None):
     return loss, stats
 
 
-def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None):
+def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None, global_images=None):
     """per_image=True Lovasz-Softmax over a batch sharded across ranks: each rank passes its own
     images; every rank gets the global loss; gradients stay local.  The finalize kernel writes the
     partial buffer ``[sum of image losses, image count, class loss sums, class presence counts]``
-    and the autograd Function all-reduces it once (csrc/lovasz.cu k_finalize, lovasz_loss.py)."""
+    and the autograd Function all-reduces it once (csrc/lovasz.cu k_finalize, lovasz_loss.py).
+
+    ``global_images`` (the batch size summed over the ranks, when the caller knows it - a fixed
+    per-rank batch): the gradient then does not depend on the collective at all, so the all-reduce is
+    issued asynchronously and the ranks no longer meet at a barrier inside every step.  The returned
+    loss is this rank's share ``sum(local image losses) / global_images`` (the shares sum to the global
+    loss; gradients are identical); ``stats["loss"]`` is the global loss and waits for the collective."""
     from .lovasz_loss import lovasz_softmax
 
     loss, outs = lovasz_softmax(probas_local, labels_local, per_image=True, ignore=ignore, return_outputs=True,
-                                shard_group=True if group is None else group)
+                                shard_group=True if group is None else group, global_images=global_images)
     return loss, _ShardStats(outs, probas_local.size(1))
 
 
@@ -97,7 +103,8 @@ class _ShardStats(dict):
     def __missing__(self, key):
         packed, c = self._outs.packed, self._c
         counts = packed[2 + c:]
-        vals = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
+        vals = dict(images=packed[1], loss=(packed[0] / packed[1]).float(),
+                    class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
         self.update(vals)
         return vals[key]
 

@@ -84,6 +84,7 @@ class LovaszOutputs:
 
     def __init__(self, buf, groups, classes):
         self._buf, self._g, self._c = buf, groups, classes
+        self._work = None    # pending asynchronous all-reduce of `packed` (sharded forward with global_images)
         g, c = groups, classes
         o = 8 * (2 + 2 * c)
         self._off = dict(packed=(0, 2 + 2 * c, torch.float64), loss=(o, 1, torch.float32),
@@ -104,7 +105,13 @@ class LovaszOutputs:
         off, n, dt = self._off[name]
         return self._buf[off:off + n * dt.itemsize].view(dt)
 
-    packed = property(lambda self: self._view("packed"))
+    def _packed(self):
+        if self._work is not None:          # make the current stream wait for the collective, once
+            self._work.wait()
+            self._work = None
+        return self._view("packed")
+
+    packed = property(_packed)
     loss = property(lambda self: self._view("loss")[0])
     label_errors = property(lambda self: self._view("label_errors"))
     loss_ce = property(lambda self: self._view("loss_ce")[0])        # hybrid path only
@@ -195,13 +202,16 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
     return outs.loss, (unit, codes), outs, ws
 
 
+_pending_reduce = {}   # device index -> LovaszOutputs whose asynchronous all-reduce may still be in flight
+
+
 class _LovaszSoftmaxFunction(torch.autograd.Function):
     """autograd hook around rtda_lovasz_fwd / rtda_lovasz_bwd.  With ``shard_group`` set
     (per_image over a batch sharded across ranks) the forward adds ONE all-reduce(sum) of the
     packed partials and returns the global mean; the backward needs no collective."""
 
     @staticmethod
-    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group):
+    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None):
         need_grad = bool(ctx.needs_input_grad[0])
         loss, (unit, codes), outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
         if holder is not None:
@@ -213,9 +223,23 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
             import torch.distributed as dist
 
             packed = outs.packed
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=None if shard_group is True else shard_group)
-            loss = (packed[0] / packed[1]).float()
-            ctx.shard_scale = (float(probas.size(0)) / packed[1]).float()   # B_local / B_global, on the device
+            grp = None if shard_group is True else shard_group
+            if global_images is None:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=grp)
+                loss = (packed[0] / packed[1]).float()
+                ctx.shard_scale = (float(probas.size(0)) / packed[1]).float()   # B_local / B_global, on the device
+            else:
+                # the global image count is known: nothing on this rank's data path depends on the
+                # collective.  The forward returns this rank's SHARE of the global mean (the shares sum
+                # to it), the all-reduce runs asynchronously and is waited for only when the reduced
+                # statistics are read (outs.packed) - ranks do not meet at a barrier every step.
+                loss = (packed[0].clone() / float(global_images)).float()
+                prev = _pending_reduce.pop(probas.device.index, None)
+                if prev is not None and prev._work is not None:
+                    prev._packed()                      # at most one collective in flight per device (stream-side wait only)
+                outs._work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+                _pending_reduce[probas.device.index] = outs
+                ctx.shard_scale = float(probas.size(0)) / float(global_images)
         if need_grad:
             ctx.save_for_backward(unit, codes, outs.class_present, outs.n_present)
         return loss
@@ -237,7 +261,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
             go.data_ptr(), unit.data_ptr(), codes.data_ptr(), present.data_ptr(), n_present.data_ptr(),
             b, c, h * w, int(ctx.per_image), grad.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
-        return grad, None, None, None, None, None
+        return grad, None, None, None, None, None, None
 
 
 def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
@@ -259,7 +283,7 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
 
 
 def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
-                   validate_labels=False, return_outputs=False, shard_group=None):
+                   validate_labels=False, return_outputs=False, shard_group=None, global_images=None):
     """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
     computes, lovasz_loss.py:185-200).
 
@@ -267,7 +291,9 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
     ``classes`` accepts 'present' and 'all'; the reference skips foreground-less
     classes unconditionally (:167-168) so both average over present classes.
     ``shard_group`` (a process group, or True for the default group) with ``per_image=True``
-    treats ``probas`` as this rank's slice of a batch sharded over the ranks (see dist.py).
+    treats ``probas`` as this rank's slice of a batch sharded over the ranks (see dist.py);
+    with ``global_images`` (the batch size over all ranks) the collective is asynchronous and the
+    returned loss is this rank's share of the global mean.
     """
     if classes not in ("present", "all"):
         raise ValueError("classes must be 'present' or 'all'")
@@ -277,7 +303,7 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
     if shard_group is not None and not per_image:
         raise ValueError("only per_image=True shards over ranks (global mode needs one sort over all pixels)")
     holder = []
-    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group)
+    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group, global_images)
     outs = holder[0]
     if validate_labels:
         bad = int(outs.label_errors.item())

@@ -13,8 +13,13 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 if len(sys.argv) > 3:
     rtda.set_sort_path(sys.argv[3])
-shape = {"c1": (1, 512, 1024, False), "c2": (4, 512, 1024, False), "c3": (4, 720, 1280, True)}[wl]
+shape = {"c1": (1, 512, 1024, False), "c2": (4, 512, 1024, False), "c3": (4, 720, 1280, True),
+         "small": (2, 128, 256, False), "small_pi": (3, 96, 160, True), "ties": (2, 128, 256, False)}[wl]
 pr, lb = synthetic.confident_case(shape[0], shape[1], shape[2], seed=11, device="cuda")
+if wl == "ties":            # one class constant (massive ties -> LSD fallback for it), twins elsewhere (slot sharing)
+    pr[:, 3] = 0.125
+    pr[..., 1::2] = pr[..., 0::2]
+    lb[..., 1::2] = lb[..., 0::2]
 p = pr.requires_grad_(True)
 for _ in range(steps):
     loss = rtda.lovasz_softmax(p, lb, ignore=255, per_image=shape[3])

@@ -310,3 +310,36 @@ def test_mixed_segments_some_fall_back(sort_path):
     if sort_path == "bucket":
         fb = rtda.segment_sort_paths((2, 6, 96, 96), False).cpu().numpy().ravel()
         assert fb[3] == 1 and fb.sum() == 1, fb
+
+
+def test_bucket_path_every_element_shares_a_slot(sort_path):
+    """Every key appears exactly twice (pixel pairs with identical probabilities and labels): all
+    elements of a bucket share their fine slot with a twin, far more than the dense list of
+    k_local holds (1024), so the in-place ordering path runs too.  Still the bucket path, still exact."""
+    probas, labels = synthetic.confident_case(1, 256, 512, seed=41)
+    probas[..., 1::2] = probas[..., 0::2]
+    labels[..., 1::2] = labels[..., 0::2]
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="twins")
+    if sort_path == "bucket":
+        assert int(rtda.segment_sort_paths((1, 19, 256, 512), False).sum()) == 0
+
+
+def test_bucket_path_sample_misleads_the_partition(sort_path):
+    """k_split samples one run of 32 pixels of every 16 (run (7u mod 16) of group u).  Here the sampled
+    pixels are diffuse and all the others sit in a narrow band of probabilities, so the sampled CDF
+    is wrong, bucket regions overflow in k_part and the segments fall back to the LSD path on the
+    device - the result must not change."""
+    b, c, h, w = 1, 19, 512, 1024
+    g = torch.Generator().manual_seed(43)
+    n = h * w
+    run = torch.arange(n) // 32
+    sampled = (run % 16) == ((run // 16) * 7) % 16
+    narrow = torch.randn((c, n), generator=g) * 0.01                      # nearly uniform softmax: errors in a narrow band
+    wide = torch.randn((c, n), generator=g) * 4.0
+    logits = torch.where(sampled[None, :], wide, narrow).view(1, c, h, w)
+    probas = torch.softmax(logits, 1)
+    labels = torch.randint(0, c, (b, h, w), generator=g)
+    labels[torch.rand((b, h, w), generator=g) < 0.1] = 255
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="misleading sample")
+    if sort_path == "bucket":
+        assert int(rtda.segment_sort_paths((b, c, h, w), False).sum()) > 0   # at least one segment had to fall back

@@ -35,6 +35,12 @@ def _worker(rank, world, port, out_dir):
         p = probas[lo:hi].cuda().requires_grad_(True)
         loss, stats = lovasz_softmax_sharded(p, labels[lo:hi].cuda(), ignore=255)
         (loss * 3.0).backward()
+        # known global batch size: asynchronous collective, the forward returns this rank's share
+        p2 = probas[lo:hi].cuda().requires_grad_(True)
+        share, stats2 = lovasz_softmax_sharded(p2, labels[lo:hi].cuda(), ignore=255, global_images=b)
+        (share * 3.0).backward()
+        share_sum = share.detach().double().clone()
+        dist.all_reduce(share_sum)
         lab, prd = synthetic.validation_maps(3 * world, 128, 160, seed=92)
         lo2, hi2 = shard_range(3 * world, rank, world)
         cm = rtda.ConfusionMatrix(19, 255)
@@ -43,7 +49,8 @@ def _worker(rank, world, port, out_dir):
         cm.all_reduce()
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss.detach().cpu().numpy(), grad=p.grad.cpu().numpy(),
-                 hist=cm.compute(), images=stats["images"].cpu().numpy(), lo=lo, hi=hi)
+                 hist=cm.compute(), images=stats["images"].cpu().numpy(), lo=lo, hi=hi,
+                 grad2=p2.grad.cpu().numpy(), share_sum=share_sum.cpu().numpy(), loss2=stats2["loss"].cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -73,3 +80,7 @@ def test_sharded_paths_match_single_gpu_and_oracle(tmp_path):
         # the local scale is (3/B_global)/K computed in a different association order than the oracle's: 1-2 ulp
         assert np.abs(z["grad"] - want["grad"][lo:hi]).max() <= 1e-6 * gmax
         assert np.array_equal(z["hist"], want_hist)                                   # counts are exact
+        # asynchronous mode: the shares sum to the global loss, the lazily reduced loss equals it, same gradients
+        assert float(z["share_sum"]) == pytest.approx(float(want["loss"]), rel=2e-6)
+        assert float(z["loss2"]) == pytest.approx(float(want["loss"]), rel=2e-6)
+        assert np.abs(z["grad2"] - want["grad"][lo:hi]).max() <= 1e-6 * gmax
