@@ -244,18 +244,28 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         u32 code[kPItems];
         // the probability is loaded whether or not the pixel turns out to be ignored: the two loads
         // are independent, so a tile waits for one global-memory latency, not two
+        const u32 hw_tile = tile_base % HW;
+        if (count == (u32)kPTile && hw_tile + (u32)kPTile <= HW) {
+            // full tile inside one image (the common case): fixed offsets, no predicates
 #pragma unroll
-        for (int j = 0; j < kPItems; ++j) {
-            const bool in = idx0 + 32 * j < count;
-            p[j] = 0.0f;
-            code[j] = 255u;
-            if (in) {
+            for (int j = 0; j < kPItems; ++j) {
                 code[j] = cg[32 * j];
-                p[j] = ld_stream_f1(pp);
+                p[j] = ld_stream_f1(pp + 32 * j);
             }
-            pp += 32;
-            hw += 32;
-            while (hw >= HW) { hw -= HW; pp += wrap; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPItems; ++j) {
+                const bool in = idx0 + 32 * j < count;
+                p[j] = 0.0f;
+                code[j] = 255u;
+                if (in) {
+                    code[j] = cg[32 * j];
+                    p[j] = ld_stream_f1(pp);
+                }
+                pp += 32;
+                hw += 32;
+                while (hw >= HW) { hw -= HW; pp += wrap; }
+            }
         }
         for (u32 b = tid; b < NB; b += kPThreads) sm_cnt[b] = 0;
         float *ug = unit_grad ? unit_grad + seg_off : nullptr;
