@@ -85,11 +85,17 @@ __device__ __forceinline__ u32 table_bin(u32 key) { return tau_of(key) >> 19; }
 // builds the map.
 __global__ void __launch_bounds__(kSplitThreads)
 k_split(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
-        const u32 *__restrict__ seg_fg, int force_lsd, u32 *__restrict__ ghist /*[S][kTabBins + 2], zeroed*/,
+        const u32 *__restrict__ seg_fg, int force_lsd, u32 *__restrict__ ghist /*[S][kSplitWords], zeroed*/,
         u32 *__restrict__ table, u32 *__restrict__ nb_out, u32 *__restrict__ fb_flag, u32 *__restrict__ fb_any) {
-    __shared__ u32 hist[kTabBins];
+    // hist: sample count per bin.  first / same: the first key seen in the bin and how many samples
+    // carried exactly that key - many samples with ONE key value are a massive exact tie (saturated
+    // probabilities: p rounds to 1 - k * 2^-24; constant / one-hot inputs) that no monotone map of the
+    // key can split; such segments go to the LSD path right away instead of failing in k_part / k_local.
+    // (A heuristic that only chooses the path: a tie it misses is caught later, at a higher cost.)
+    extern __shared__ u32 split_smem[];
+    u32 *hist = split_smem, *first = split_smem + kTabBins, *same = split_smem + 2 * kTabBins;
     __shared__ u32 wtmp[kSplitThreads / 32];
-    __shared__ u32 s_mvalid, s_last;
+    __shared__ u32 s_mvalid, s_last, s_heavy;
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 seg = blockIdx.x;
     const u32 g = seg / (u32)geo.C, c = seg - g * (u32)geo.C;
@@ -103,9 +109,10 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     }
     // (the sample is binned in shared memory first: direct reductions on the global histogram were
     // measured slower, 69 vs 34 us at c2 - the populated bins are few and hot)
-    u32 *gh = ghist + (size_t)seg * (kTabBins + 2);
-    for (int i = tid; i < kTabBins; i += kSplitThreads) hist[i] = 0;
-    if (tid == 0) s_mvalid = 0;
+    u32 *gh = ghist + (size_t)seg * kSplitWords;
+    u32 *gfirst = gh + kTabBins + 2, *gsame = gfirst + kTabBins;
+    for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = 0; first[i] = 0; same[i] = 0; }
+    if (tid == 0) { s_mvalid = 0; s_heavy = 0; }
     __syncthreads();
     const u32 n = (u32)geo.n, HW = (u32)geo.HW;
     u32 mvalid = 0;
@@ -128,7 +135,10 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
             u32 neg;
             const u32 key = error_key(p, true, code == c, &neg);
             if (key == 0xFFFFFFFFu) continue;          // error exactly 0: never sorted
-            atomicAdd(&hist[table_bin(key)], 1u);
+            const u32 bin = table_bin(key);
+            atomicAdd(&hist[bin], 1u);
+            const u32 old = atomicCAS(&first[bin], 0u, key);       // (key != 0: errors are below 2^32 - 1)
+            if (old == 0u || old == key) atomicAdd(&same[bin], 1u);
         }
     }
 #pragma unroll
@@ -136,8 +146,13 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     if (lane == 0 && mvalid) atomicAdd(&s_mvalid, mvalid);
     __syncthreads();
     if (gridDim.y > 1) {
-        for (int i = tid; i < kTabBins; i += kSplitThreads)
-            if (hist[i]) atomicAdd(&gh[i], hist[i]);
+        for (int i = tid; i < kTabBins; i += kSplitThreads) {
+            if (hist[i]) {
+                atomicAdd(&gh[i], hist[i]);
+                const u32 old = atomicCAS(&gfirst[i], 0u, first[i]);
+                if (old == 0u || old == first[i]) atomicAdd(&gsame[i], same[i]);
+            }
+        }
         if (tid == 0 && s_mvalid) atomicAdd(&gh[kTabBins], s_mvalid);
         __threadfence();
         __syncthreads();
@@ -145,9 +160,23 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        for (int i = tid; i < kTabBins; i += kSplitThreads) hist[i] = ld_relaxed(&gh[i]);
+        for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = ld_relaxed(&gh[i]); same[i] = ld_relaxed(&gsame[i]); }
         if (tid == 0) s_mvalid = ld_relaxed(&gh[kTabBins]);
         __syncthreads();
+    }
+    {
+        // one key value filling more than about half a bucket region: its bucket would overflow
+        u32 SG = (u32)geo.n / 16384u;
+        SG = SG < 1u ? 1u : (SG > (u32)kSampleStride ? (u32)kSampleStride : SG);
+        bool heavy = false;
+        for (int i = tid; i < kTabBins; i += kSplitThreads)
+            heavy |= same[i] * SG > (u32)(kBTile - kBMean);
+        if (heavy) s_heavy = 1u;
+        __syncthreads();
+        if (s_heavy) {
+            if (tid == 0) { nb_out[seg] = 0; fb_flag[seg] = 1u; *fb_any = 1u; }
+            return;
+        }
     }
     constexpr int kPerT = kTabBins / kSplitThreads;
     u32 h[kPerT], hsum = 0;
@@ -388,7 +417,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 // direct comparison of (key, pixel index).  The counters are W-bit fields packed in 32-bit words
 // (one shared-memory atomic per element returns the arrival ticket); W = 4 first, and if a field
 // overflows (16 or more elements in one slot: exact ties) the block starts over with W = 8 (16384
-// slots); 256 or more raises the segment's fallback flag.
+// slots); with 256 or more in one slot the block sorts its whole bucket with a bitonic network instead.
 constexpr int kCntWords = 4096;          // 16 KB of packed counters: 32768 4-bit or 16384 8-bit fine slots
 constexpr int kColMax = 1024;            // dense list of the elements that share a fine slot
 struct LocalShared {
@@ -568,6 +597,38 @@ __device__ __forceinline__ void local_reset(LocalShared &sm) {
     if (threadIdx.x == 0) sm.ncol = 0;
 }
 
+// Full in-place sort of the staged bucket by (key, pixel index): bitonic network over the next power
+// of two (padding sorts last).  ~90 barrier-separated stages for 8192 elements - only for buckets
+// whose fine-slot counters overflowed twice.  Leaves the bucket sorted (rank = position) and the
+// foreground bitmap filled.
+__device__ __noinline__ void local_sort_all(LocalShared &sm, u32 cnt) {
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u64 cmp_mask = ~((u64)(kPayloadFg | kPayloadNeg));
+    u32 N = 32;
+    while (N < cnt) N <<= 1;
+    __syncthreads();
+    for (u32 i = cnt + tid; i < N; i += kBThreads) sm.stage[i] = ~0ull;
+    __syncthreads();
+    for (u32 k = 2; k <= N; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 t = tid; t < N / 2; t += kBThreads) {
+                const u32 i = 2u * t - (t & (j - 1u));
+                const u32 l = i + j;
+                const u64 a = sm.stage[i], b = sm.stage[l];
+                const bool up = (i & k) == 0u;
+                if (((a & cmp_mask) > (b & cmp_mask)) == up) { sm.stage[i] = b; sm.stage[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (u32 q = tid; q < N; q += kBThreads) {       // N is a multiple of 32: whole warps
+        const bool fg = q < cnt && ((u32)sm.stage[q] & kPayloadFg);
+        const u32 m = __ballot_sync(RTDA_FULL_MASK, fg);
+        if (lane == 0) sm.fgbits[q >> 5] = m;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u64 *__restrict__ cursor, u32 *__restrict__ fb_flag,
@@ -613,9 +674,12 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     if (!local_ranks<4>(sm, tab, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8>(sm, tab, cnt, xmax, rk)) {   // 256 or more exact ties: the LSD path redoes the segment
-            if (tid == 0) { fb_flag[seg] = 1u; *fb_any = 1u; }
-            return;
+        if (!local_ranks<8>(sm, tab, cnt, xmax, rk)) {
+            // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
+            // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
+            local_sort_all(sm, cnt);
+#pragma unroll
+            for (int j = 0; j < kBItems; ++j) rk[j] = j * kBThreads + tid;
         }
     }
     const u32 base_cnt = (u32)sm.base, base_fg = (u32)(sm.base >> 32);

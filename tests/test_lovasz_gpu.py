@@ -343,3 +343,18 @@ def test_bucket_path_sample_misleads_the_partition(sort_path):
     assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="misleading sample")
     if sort_path == "bucket":
         assert int(rtda.segment_sort_paths((b, c, h, w), False).sum()) > 0   # at least one segment had to fall back
+
+
+def test_bucket_path_more_than_1024_buckets(sort_path):
+    """A 6.3 Mpixel segment needs about 1100 buckets: k_part's claim loop beyond its four unrolled
+    claims per thread, 12-bit bucket ids in the exchanged payload, a 1.1 k-entry cursor scan in k_local."""
+    b, c, h, w = 1, 3, 2048, 3072
+    probas, labels = synthetic.diffuse_case(b, h, w, n_class=c, seed=51, device="cuda")
+    assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, False, tag="6.3 Mpx diffuse")
+    if sort_path == "bucket":
+        assert int(rtda.segment_sort_paths((b, c, h, w), False).sum()) == 0
+    # the same size with saturated 3-class predictions: thousands of foreground pixels share the errors
+    # k * 2^-24 (p rounds to 1 - k * 2^-24), more than a fine slot's 8-bit counter holds, so these
+    # segments are redone by the LSD path - same bits either way
+    probas, labels = synthetic.confident_case(b, h, w, n_class=c, seed=51, device="cuda")
+    assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, False, tag="6.3 Mpx saturated")
