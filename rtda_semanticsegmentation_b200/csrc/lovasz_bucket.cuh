@@ -28,7 +28,7 @@
 // Elements with error exactly 0 are not sorted at all: they sit behind every other element, contribute
 // 0 * g to the loss and sgn(0) = 0 to the gradient, and dropping a suffix changes no other rank.
 #pragma once
-// (included inside namespace rtda by lovasz.cu, after error_key / div_rn_counts / loss_term_fix)
+// (included inside namespace rtda by lovasz.cu, after error_key / div_rn_counts / LossAcc)
 
 template <int NW, typename T>
 __device__ __forceinline__ T block_excl_scan(T v, T *warp_tmp /*[NW]*/, T *total) {
@@ -65,37 +65,64 @@ __device__ __forceinline__ u32 tau_of(u32 key) {
     return eb >= 0x3F000000u ? __float_as_uint(__fsub_rn(1.0f, __uint_as_float(eb))) : 0x7E000000u - eb;
 }
 
-// Monotone map key -> position in the sampled cumulative distribution, in units of buckets, 16.16 fixed
-// point: the top 12 bits of tau select a table interval [tab[p], tab[p+1]), its low 19 bits
-// interpolate inside it.  Integer part = bucket, fractional part = position inside the bucket
-// (level 2 turns it into a fine slot).
-__device__ __forceinline__ u32 cdf_pos(u32 key, const u32 *tab, u32 xmax) {
+// Monotone map (key, pixel index) -> position in the sampled cumulative distribution, in units of
+// buckets, 16.16 fixed point: the top 12 bits of tau select a table interval [tab[p], tab[p+1]), its
+// low 19 bits interpolate inside it.  Integer part = bucket, fractional part = position inside the
+// bucket (level 2 turns it into a fine slot).
+//
+// Boundary ties.  Saturated predictions put thousands of elements on a handful of keys: a foreground
+// probability that rounded to 1 - k * 2^-24 has the error k * 2^-24 exactly, and for small k that
+// value has an all-zero low mantissa, i.e. it is the FIRST key of its table interval (low 19 bits of
+// tau = 0).  k_split counts the samples sitting exactly there; when they are many the interval is
+// flagged (bit 31 of tab[p]) and ties[p] holds the width T, in the same units, that those elements
+// deserve.  They are then spread over [x0, x0 + T) by pixel index - which is their sort order - and
+// the other keys of the interval share [x0 + T, x0 + dx).  So a tie of any size is split across
+// buckets and fine slots instead of overflowing one.
+constexpr u32 kTabTie = 1u << 31;
+__device__ __forceinline__ u32 cdf_pos_ties(u32 key, u32 idx, u32 n, const u32 *tab, const u32 *__restrict__ ties, u32 xmax) {
     const u32 tau = tau_of(key);
     const u32 p = tau >> 19;                         // <= 0x7E0 << 1 = 4032
-    const u32 x0 = tab[p], dx = tab[p + 1] - x0;
-    const u32 x = x0 + __umulhi(tau << 13, dx);      // (low19 * dx) >> 19
+    const u32 t0 = tab[p];
+    const u32 x0 = t0 & ~kTabTie;
+    u32 dx = (tab[p + 1] & ~kTabTie) - x0;
+    u32 x = x0;
+    if (t0 & kTabTie) {
+        const u32 T = ties[p];
+        if ((tau & 0x7FFFFu) == 0u) return x0 + (u32)(((u64)idx * T) / n);     // < x0 + T <= x0 + dx
+        x += T;
+        dx -= T;
+    }
+    x += __umulhi(tau << 13, dx);                    // (low19 * dx) >> 19
     return x < xmax ? x : xmax;
 }
-
-__device__ __forceinline__ u32 table_bin(u32 key) { return tau_of(key) >> 19; }
+// The same map for a segment without flagged intervals (the table then carries no flag bits).
+__device__ __forceinline__ u32 cdf_pos_plain(u32 key, const u32 *tab, u32 xmax) {
+    const u32 tau = tau_of(key);
+    const u32 p = tau >> 19;
+    const u32 x0 = tab[p], dx = tab[p + 1] - x0;
+    const u32 x = x0 + __umulhi(tau << 13, dx);
+    return x < xmax ? x : xmax;
+}
+__device__ __forceinline__ u32 cdf_pos(bool has_ties, u32 key, u32 idx, u32 n, const u32 *tab, const u32 *__restrict__ ties, u32 xmax) {
+    return has_ties ? cdf_pos_ties(key, idx, n, tab, ties, xmax) : cdf_pos_plain(key, tab, xmax);
+}
+constexpr u32 kNbTies = 1u << 31;                    // bit of nb[seg]: the segment's map has flagged intervals
 
 // ---------------------------------------------------------------------------
 // k_split: sample histogram -> cumulative map of one segment.  gridDim.y blocks share a segment:
 // each adds its part of the sample to the segment's global histogram, the last one to finish
 // builds the map.
-__global__ void __launch_bounds__(kSplitThreads)
+__global__ void __launch_bounds__(kSplitThreads, 2)
 k_split(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
         const u32 *__restrict__ seg_fg, int force_lsd, u32 *__restrict__ ghist /*[S][kSplitWords], zeroed*/,
-        u32 *__restrict__ table, u32 *__restrict__ nb_out, u32 *__restrict__ fb_flag, u32 *__restrict__ fb_any) {
-    // hist: sample count per bin.  first / same: the first key seen in the bin and how many samples
-    // carried exactly that key - many samples with ONE key value are a massive exact tie (saturated
-    // probabilities: p rounds to 1 - k * 2^-24; constant / one-hot inputs) that no monotone map of the
-    // key can split; such segments go to the LSD path right away instead of failing in k_part / k_local.
-    // (A heuristic that only chooses the path: a tie it misses is caught later, at a higher cost.)
+        u32 *__restrict__ table, u32 *__restrict__ ties, u32 *__restrict__ nb_out, u32 *__restrict__ fb_flag,
+        u32 *__restrict__ fb_any) {
+    // hist: sample count per bin.  zc: how many of them sit exactly on the bin's first key (low 19
+    // bits of tau = 0): the boundary ties cdf_pos spreads by pixel index.
     extern __shared__ u32 split_smem[];
-    u32 *hist = split_smem, *first = split_smem + kTabBins, *same = split_smem + 2 * kTabBins;
+    u32 *hist = split_smem, *zc = split_smem + kTabBins;
     __shared__ u32 wtmp[kSplitThreads / 32];
-    __shared__ u32 s_mvalid, s_last, s_heavy;
+    __shared__ u32 s_mvalid, s_last;
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 seg = blockIdx.x;
     const u32 g = seg / (u32)geo.C, c = seg - g * (u32)geo.C;
@@ -110,9 +137,9 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     // (the sample is binned in shared memory first: direct reductions on the global histogram were
     // measured slower, 69 vs 34 us at c2 - the populated bins are few and hot)
     u32 *gh = ghist + (size_t)seg * kSplitWords;
-    u32 *gfirst = gh + kTabBins + 2, *gsame = gfirst + kTabBins;
-    for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = 0; first[i] = 0; same[i] = 0; }
-    if (tid == 0) { s_mvalid = 0; s_heavy = 0; }
+    u32 *gzc = gh + kTabBins + 2;
+    for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = 0; zc[i] = 0; }
+    if (tid == 0) s_mvalid = 0;
     __syncthreads();
     const u32 n = (u32)geo.n, HW = (u32)geo.HW;
     u32 mvalid = 0;
@@ -135,10 +162,10 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
             u32 neg;
             const u32 key = error_key(p, true, code == c, &neg);
             if (key == 0xFFFFFFFFu) continue;          // error exactly 0: never sorted
-            const u32 bin = table_bin(key);
+            const u32 tau = tau_of(key);
+            const u32 bin = tau >> 19;
             atomicAdd(&hist[bin], 1u);
-            const u32 old = atomicCAS(&first[bin], 0u, key);       // (key != 0: errors are below 2^32 - 1)
-            if (old == 0u || old == key) atomicAdd(&same[bin], 1u);
+            if ((tau & 0x7FFFFu) == 0u) atomicAdd(&zc[bin], 1u);
         }
     }
 #pragma unroll
@@ -149,8 +176,7 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         for (int i = tid; i < kTabBins; i += kSplitThreads) {
             if (hist[i]) {
                 atomicAdd(&gh[i], hist[i]);
-                const u32 old = atomicCAS(&gfirst[i], 0u, first[i]);
-                if (old == 0u || old == first[i]) atomicAdd(&gsame[i], same[i]);
+                if (zc[i]) atomicAdd(&gzc[i], zc[i]);
             }
         }
         if (tid == 0 && s_mvalid) atomicAdd(&gh[kTabBins], s_mvalid);
@@ -160,23 +186,9 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = ld_relaxed(&gh[i]); same[i] = ld_relaxed(&gsame[i]); }
+        for (int i = tid; i < kTabBins; i += kSplitThreads) { hist[i] = ld_relaxed(&gh[i]); zc[i] = ld_relaxed(&gzc[i]); }
         if (tid == 0) s_mvalid = ld_relaxed(&gh[kTabBins]);
         __syncthreads();
-    }
-    {
-        // one key value filling more than about half a bucket region: its bucket would overflow
-        u32 SG = (u32)geo.n / 16384u;
-        SG = SG < 1u ? 1u : (SG > (u32)kSampleStride ? (u32)kSampleStride : SG);
-        bool heavy = false;
-        for (int i = tid; i < kTabBins; i += kSplitThreads)
-            heavy |= same[i] * SG > (u32)(kBTile - kBMean);
-        if (heavy) s_heavy = 1u;
-        __syncthreads();
-        if (s_heavy) {
-            if (tid == 0) { nb_out[seg] = 0; fb_flag[seg] = 1u; *fb_any = 1u; }
-            return;
-        }
     }
     constexpr int kPerT = kTabBins / kSplitThreads;
     u32 h[kPerT], hsum = 0;
@@ -197,15 +209,29 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     // cumulative map with a floor of 1/kPrior sample per bin: a bin the sample missed still gets a
     // little width, so the elements that do fall there spread over slots instead of piling into one
     u32 *tab = table + (size_t)seg * (kTabBins + 1);
+    u32 *tie = ties + (size_t)seg * kTabBins;
     const u64 scale = (u64)NB << 16;
     const u64 denom = (u64)kPrior * m_nz + kTabBins;
     u64 cum = (u64)kPrior * excl + (u64)kPerT * tid;
+    u32 SG = (u32)geo.n / 16384u;
+    SG = SG < 1u ? 1u : (SG > (u32)kSampleStride ? (u32)kSampleStride : SG);
+    bool any_tie = false;
 #pragma unroll
     for (int k = 0; k < kPerT; ++k) {
-        tab[kPerT * tid + k] = (u32)((cum * scale) / denom);
+        const u32 bin = kPerT * tid + k;
+        const u32 z = zc[bin];
+        // boundary ties worth spreading: an estimated kTieMin elements or more on one key (smaller
+        // ties are a bucket's own business: 8-bit slot counters, else its bitonic sort).  Never bin 0:
+        // tau = 0 is shared by the error 1.0 and by garbage (errors above 1).
+        const bool spread = bin != 0u && z * SG >= (u32)kTieMin;
+        const u32 T = spread ? (u32)(((u64)kPrior * z * scale) / denom) : 0u;
+        tab[bin] = (u32)((cum * scale) / denom) | (T ? kTabTie : 0u);
+        tie[bin] = T;
+        any_tie |= T != 0u;
         cum += (u64)kPrior * h[k] + 1u;
     }
-    if (tid == 0) { tab[kTabBins] = (u32)scale; nb_out[seg] = NB; }
+    const int seg_ties = __syncthreads_or(any_tie);
+    if (tid == 0) { tab[kTabBins] = (u32)scale; nb_out[seg] = NB | (seg_ties ? kNbTies : 0u); }
 }
 
 // ---------------------------------------------------------------------------
@@ -225,9 +251,9 @@ static inline size_t part_smem_bytes(int nbk) {
 
 __global__ void __launch_bounds__(kPThreads, 4)
 k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
-       const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ nb,
-       u64 *__restrict__ cursor, u64 *__restrict__ out, u32 *__restrict__ fb_flag, u32 *__restrict__ fb_any,
-       float *__restrict__ unit_grad) {
+       const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ ties,
+       const u32 *__restrict__ nb, u64 *__restrict__ cursor, u64 *__restrict__ out, u32 *__restrict__ fb_flag,
+       u32 *__restrict__ fb_any, float *__restrict__ unit_grad) {
     extern __shared__ __align__(16) unsigned char part_smem[];
     PartShared &sm = *reinterpret_cast<PartShared *>(part_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -239,12 +265,15 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     if (tid == 0) sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
     __syncthreads();
     if (sm.skip) return;
-    const u32 NB = nb[seg];
+    const u32 nb_raw = nb[seg];
+    const u32 NB = nb_raw & ~kNbTies;
+    const bool has_ties = (nb_raw & kNbTies) != 0u;
     const u32 xmax = (NB << 16) - 1u;
     u32 *sm_cnt = sm.arrays;
     u32 *sm_pre = sm.arrays + ((u32)geo.NBK + kPThreads - 1) / kPThreads * kPThreads;
     const u32 n = (u32)geo.n;
     const size_t seg_off = (size_t)seg * n;
+    const u32 *tie = ties + (size_t)seg * kTabBins;         // read through L1: touched only for flagged intervals
     {
         const u32 *tsrc = table + (size_t)seg * (kTabBins + 1);
         for (u32 k = tid; k < (u32)kTabBins + 1u; k += kPThreads) sm.tab[k] = tsrc[k];
@@ -312,12 +341,23 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     }
     __syncthreads();
 
+    if (!has_ties) {                                 // block-uniform: the common case keeps the short map
 #pragma unroll
-    for (int j = 0; j < kPItems; ++j) {
-        if (st[j] & kLive) {
-            const u32 b = cdf_pos(key[j], sm.tab, xmax) >> 16;
-            const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] & kPayloadFg) ? 0x10000u : 0u));
-            st[j] |= (b << 16) | (old & 0xffffu);
+        for (int j = 0; j < kPItems; ++j) {
+            if (st[j] & kLive) {
+                const u32 b = cdf_pos_plain(key[j], sm.tab, xmax) >> 16;
+                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] & kPayloadFg) ? 0x10000u : 0u));
+                st[j] |= (b << 16) | (old & 0xffffu);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPItems; ++j) {
+            if (st[j] & kLive) {
+                const u32 b = cdf_pos_ties(key[j], i0 + 32 * j, n, sm.tab, tie, xmax) >> 16;
+                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] & kPayloadFg) ? 0x10000u : 0u));
+                st[j] |= (b << 16) | (old & 0xffffu);
+            }
         }
     }
     __syncthreads();
@@ -431,7 +471,7 @@ struct LocalShared {
     u32 scan_tmp[kBWarps];
     u32 woff[kBWarps];
     u64 red64[kBWarps];
-    long long red[kBWarps];
+    long long red[2][kBWarps];
     u64 mbar;
     u64 base;
     u32 ncol;
@@ -465,8 +505,8 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 // One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
 // rk[j] ends as the local rank of element j * kBThreads + tid.
 template <int W>
-__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, u32 cnt, u32 xmax,
-                                            u32 (&rk)[kBItems]) {
+__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
+                                            bool has_ties, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
     constexpr u32 FW = 32 / W;                       // fields per word
     constexpr u32 FM = (1u << W) - 1u;               // largest field value
     constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
@@ -481,7 +521,8 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
         if (j * kBThreads >= cnt) continue;          // block-uniform: the bucket is smaller than its capacity
         if (idx < cnt) {
             // the keys of one bucket share a few table entries: the loads broadcast out of L1
-            const u32 f = (cdf_pos((u32)(sm.stage[idx] >> 32), tab, xmax) & 0xffffu) >> FSHIFT;
+            const u64 e = sm.stage[idx];
+            const u32 f = (cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu) >> FSHIFT;
             const u32 sh = (f % FW) * W;
             const u32 t = (atomicAdd(&sm.cntw[f / FW], 1u << sh) >> sh) & FM;
             over |= t == FM;                         // the field was already full: this add spilled into the next one
@@ -631,8 +672,9 @@ __device__ __noinline__ void local_sort_all(LocalShared &sm, u32 cnt) {
 
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
-        const u32 *__restrict__ table, const u64 *__restrict__ cursor, u32 *__restrict__ fb_flag,
-        u32 *__restrict__ fb_any, unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad) {
+        const u32 *__restrict__ table, const u32 *__restrict__ ties, const u64 *__restrict__ cursor,
+        u32 *__restrict__ fb_flag, u32 *__restrict__ fb_any, unsigned long long *__restrict__ seg_sum,
+        float *__restrict__ unit_grad) {
     extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -640,7 +682,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     const u32 b = blockIdx.x - seg * (u32)geo.NBK;
     const u32 G = seg_fg[seg];
     if (tid == 0) {
-        sm.skip = (G == 0 || ld_relaxed(fb_flag + seg) != 0 || b >= nb[seg]) ? 1u : 0u;
+        sm.skip = (G == 0 || ld_relaxed(fb_flag + seg) != 0 || b >= (nb[seg] & ~kNbTies)) ? 1u : 0u;
         mbar_init(&sm.mbar, 1);
     }
     __syncthreads();
@@ -651,8 +693,11 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     if (cnt == 0) return;
     // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
     if (tid == 0) bulk_load(sm.stage, regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile, ((cnt + 1u) & ~1u) * 8u, &sm.mbar);
-    const u32 xmax = (nb[seg] << 16) - 1u;
+    const u32 nb_raw = nb[seg];
+    const bool has_ties = (nb_raw & kNbTies) != 0u;
+    const u32 xmax = ((nb_raw & ~kNbTies) << 16) - 1u;
     const u32 *tab = table + (size_t)seg * (kTabBins + 1);
+    const u32 *tie = ties + (size_t)seg * kTabBins;
 
     // meanwhile: elements (low word) and foreground elements (high word) of the earlier buckets
     u64 acc64 = 0;
@@ -671,10 +716,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     mbar_wait(&sm.mbar, 0);
 
     u32 rk[kBItems];
-    if (!local_ranks<4>(sm, tab, cnt, xmax, rk)) {
+    if (!local_ranks<4>(sm, tab, tie, has_ties, (u32)geo.n, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8>(sm, tab, cnt, xmax, rk)) {
+        if (!local_ranks<8>(sm, tab, tie, has_ties, (u32)geo.n, cnt, xmax, rk)) {
             // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
             // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
             local_sort_all(sm, cnt);
@@ -692,7 +737,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
 
     // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
     float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
-    long long acc = 0;
+    LossAcc acc = {0, 0};
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
         const u32 idx = j * kBThreads + tid;
@@ -708,18 +753,17 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
             const float gr = __fsub_rn(jac, jprev);
             const float err = __uint_as_float(~(u32)(e >> 32));
-            acc += loss_term_fix(err, gr);
+            acc.add(err, gr);
             if (ug) ug[pay & kPayloadIdx] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(RTDA_FULL_MASK, acc, o);
-    if (lane == 0) sm.red[warp] = acc;
+    acc.warp_reduce();
+    if (lane == 0) { sm.red[0][warp] = acc.a; sm.red[1][warp] = acc.b; }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 2) {
         long long t = 0;
 #pragma unroll
-        for (int w = 0; w < kBWarps; ++w) t += sm.red[w];
-        atomicAdd(&seg_sum[seg], (unsigned long long)t);            // integer: the order of the adds does not matter
+        for (int w = 0; w < kBWarps; ++w) t += sm.red[tid][w];
+        atomicAdd(&seg_sum[(size_t)tid * geo.S + seg], (unsigned long long)t);    // integer: the order of the adds does not matter
     }
 }

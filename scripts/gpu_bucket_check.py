@@ -92,7 +92,7 @@ def main():
             S, NBK = int(o[14]), int(o[22])
             cur = ws[int(o[18]):int(o[18]) + 8 * S * NBK].view(torch.int64).view(S, NBK).cpu().numpy()
             occ = cur & 0xffffffff
-            nbs = ws[int(o[17]):int(o[17]) + 4 * S].view(torch.int32).cpu().numpy()
+            nbs = ws[int(o[17]):int(o[17]) + 4 * S].view(torch.int32).cpu().numpy() & 0x7fffffff
             print(f"    buckets per segment {nbs.tolist()}")
             for sgi in (0, 7):
                 o_ = occ[sgi, :nbs[sgi]]

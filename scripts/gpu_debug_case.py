@@ -23,7 +23,7 @@ _lib.load().rtda_lovasz_debug_layout(b, c, h * w, int(per_image), o)
 ws = next(iter(_workspaces.values()))
 S, NBK = int(o[14]), int(o[22])
 fb = ws[int(o[16]):int(o[16]) + 4 * S].view(torch.int32).cpu().numpy()
-nbs = ws[int(o[17]):int(o[17]) + 4 * S].view(torch.int32).cpu().numpy()
+nbs = ws[int(o[17]):int(o[17]) + 4 * S].view(torch.int32).cpu().numpy() & 0x7fffffff
 cur = ws[int(o[18]):int(o[18]) + 8 * S * NBK].view(torch.int64).view(S, NBK).cpu().numpy()
 occ = cur & 0xffffffff
 print("loss", float(loss), "S", S, "NBK", NBK, "fallback flags", fb.tolist()[:40], "buckets", nbs.tolist()[:40])

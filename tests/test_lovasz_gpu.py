@@ -303,13 +303,19 @@ def test_mixed_segments_some_fall_back(sort_path):
     g = torch.Generator().manual_seed(35)
     logits = torch.randn((2, 6, 96, 96), generator=g) * 2
     probas = torch.softmax(logits, 1)
-    probas[:, 3] = 0.125                                                   # class 3: two distinct error values
+    probas[:, 3] = 0.3                                                     # class 3: two distinct error values (not on a boundary of the map)
     labels = torch.randint(0, 6, (2, 96, 96), generator=g)
     labels[torch.rand((2, 96, 96), generator=g) < 0.1] = 255
     assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="mixed")
     if sort_path == "bucket":
         fb = rtda.segment_sort_paths((2, 6, 96, 96), False).cpu().numpy().ravel()
         assert fb[3] == 1 and fb.sum() == 1, fb
+    # the same with a constant whose errors (2^-3 and 1 - 2^-3) are first keys of their map intervals:
+    # such boundary ties are spread over the buckets by pixel index and nothing falls back
+    probas[:, 3] = 0.125
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag="mixed, boundary ties")
+    if sort_path == "bucket":
+        assert int(rtda.segment_sort_paths((2, 6, 96, 96), False).sum()) == 0
 
 
 def test_bucket_path_every_element_shares_a_slot(sort_path):
@@ -358,3 +364,15 @@ def test_bucket_path_more_than_1024_buckets(sort_path):
     # segments are redone by the LSD path - same bits either way
     probas, labels = synthetic.confident_case(b, h, w, n_class=c, seed=51, device="cuda")
     assert_matches_oracle(probas.cpu().numpy(), labels.cpu().numpy(), 255, False, tag="6.3 Mpx saturated")
+
+
+@pytest.mark.parametrize("boost,scale", [(16.0, 3.0), (20.0, 2.0)])
+def test_saturated_predictions_stay_on_the_bucket_path(sort_path, boost, scale):
+    """Saturated softmax outputs: tens of thousands of foreground errors equal k * 2^-24 exactly.  Those
+    boundary ties are spread over buckets by pixel index (their sort order), smaller tie groups are
+    sorted inside their bucket - no segment needs the LSD path, and the result is bit-exact."""
+    labels = synthetic.blocky_labels(2, 512, 512, seed=61)
+    probas = torch.softmax(synthetic.confident_logits(labels, seed=61, scale=scale, boost=boost), 1)
+    assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag=f"boost {boost}")
+    if sort_path == "bucket":
+        assert int(rtda.segment_sort_paths((2, 19, 512, 512), False).sum()) == 0
