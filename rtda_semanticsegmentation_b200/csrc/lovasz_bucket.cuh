@@ -61,8 +61,14 @@ __device__ __forceinline__ T block_excl_scan(T v, T *warp_tmp /*[NW]*/, T *total
 // piecewise-linear map models well; in the raw key the last bin under err = 1 holds a spike.
 __device__ __forceinline__ u32 tau_of(u32 key) {
     const u32 eb = ~key;                             // bits of the error
-    if (eb > 0x3F800000u) return 0u;                 // err > 1 or NaN (garbage probabilities): first
-    return eb >= 0x3F000000u ? __float_as_uint(__fsub_rn(1.0f, __uint_as_float(eb))) : 0x7E000000u - eb;
+    // both forms are evaluated (the subtraction is harmless on any bit pattern) and selected: two
+    // compares and two selects; written as a chain of `if`s the compiler emits divergence-safe branches
+    const u32 hi = __float_as_uint(__fsub_rn(1.0f, __uint_as_float(eb)));
+    const u32 lo = 0x7E000000u - eb;
+    u32 t, r;
+    asm("{\n.reg .pred p;\nsetp.ge.u32 p, %1, 0x3F000000;\nselp.u32 %0, %2, %3, p;\n}" : "=r"(t) : "r"(eb), "r"(hi), "r"(lo));
+    asm("{\n.reg .pred p;\nsetp.gt.u32 p, %1, 0x3F800000;\nselp.u32 %0, 0, %2, p;\n}" : "=r"(r) : "r"(eb), "r"(t));
+    return r;                                        // err > 1 or NaN (garbage probabilities): first
 }
 
 // Monotone map (key, pixel index) -> position in the sampled cumulative distribution, in units of
@@ -151,21 +157,36 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         const u32 runs = (n + 32u * SG - 1u) / (32u * SG);
         const unsigned char *cg = codes + (size_t)g * n;
         const u32 wpb = kSplitThreads / 32;
-        for (u32 u = blockIdx.y * wpb + (tid >> 5); u < runs; u += gridDim.y * wpb) {
-            const u32 i = 32u * SG * u + 32u * ((u * 7u) % SG) + lane;
-            if (i >= n) continue;
-            const u32 bi = i / HW, hw = i - bi * HW;
-            const u32 code = cg[i];                  // two independent loads
-            const float p = probas[(((size_t)g * geo.Bg + bi) * geo.C + c) * (size_t)HW + hw];
-            if (code == 255u) continue;
-            ++mvalid;
-            u32 neg;
-            const u32 key = error_key(p, true, code == c, &neg);
-            if (key == 0xFFFFFFFFu) continue;          // error exactly 0: never sorted
-            const u32 tau = tau_of(key);
-            const u32 bin = tau >> 19;
-            atomicAdd(&hist[bin], 1u);
-            if ((tau & 0x7FFFFu) == 0u) atomicAdd(&zc[bin], 1u);
+        // kSplitUnroll runs per warp and iteration: their loads are issued before any of them is
+        // binned, so a warp keeps that many DRAM round trips in flight instead of one
+        const u32 ustep = gridDim.y * wpb;
+        for (u32 u0 = blockIdx.y * wpb + (tid >> 5); u0 < runs; u0 += kSplitUnroll * ustep) {
+            u32 code[kSplitUnroll];
+            float p[kSplitUnroll];
+#pragma unroll
+            for (int q = 0; q < kSplitUnroll; ++q) {
+                const u32 u = u0 + (u32)q * ustep;
+                const u32 i = 32u * SG * u + 32u * ((u * 7u) % SG) + lane;
+                code[q] = 255u;
+                p[q] = 0.0f;
+                if (u < runs && i < n) {
+                    const u32 bi = i / HW, hw = i - bi * HW;
+                    code[q] = cg[i];                 // two independent loads
+                    p[q] = probas[(((size_t)g * geo.Bg + bi) * geo.C + c) * (size_t)HW + hw];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kSplitUnroll; ++q) {
+                if (code[q] == 255u) continue;
+                ++mvalid;
+                u32 neg;
+                const u32 key = error_key(p[q], true, code[q] == c, &neg);
+                if (key == 0xFFFFFFFFu) continue;      // error exactly 0: never sorted
+                const u32 tau = tau_of(key);
+                const u32 bin = tau >> 19;
+                atomicAdd(&hist[bin], 1u);
+                if ((tau & 0x7FFFFu) == 0u) atomicAdd(&zc[bin], 1u);
+            }
         }
     }
 #pragma unroll
@@ -249,7 +270,7 @@ static inline size_t part_smem_bytes(int nbk) {
     return sizeof(PartShared) + 2 * pad * sizeof(u32);
 }
 
-__global__ void __launch_bounds__(kPThreads, 4)
+__global__ void __launch_bounds__(kPThreads, kPBlocksPerSM)
 k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
        const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ ties,
        const u32 *__restrict__ nb, u64 *__restrict__ cursor, u64 *__restrict__ out, u32 *__restrict__ fb_flag,
@@ -284,8 +305,10 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 count = (n - tile_base < (u32)kPTile) ? n - tile_base : (u32)kPTile;
     __syncthreads();          // the previous tile no longer uses the shared arrays (and the map is loaded)
 
-    // per element: the key and one word of state {fg:31, neg:30, live:29, bucket:16..26, rank in (tile, bucket):0..12};
-    // the pixel index is recomputed from the element's position in the tile
+    // per element: the key and one word of state {fg:31, neg:30, live:29, bucket:P..P+10, rank in (tile, bucket):0..P-1}
+    // with P = kPPosBits (a rank is below the tile size) - the layout of the exchanged payload, so that
+    // one AND/OR builds it; the pixel index is recomputed from the element's position in the tile
+    constexpr u32 kPB = (u32)kPPosBits, kPosMask = (1u << kPB) - 1u;
     u32 key[kPItems], st[kPItems];
     const u32 idx0 = warp * (32 * kPItems) + lane;
     const u32 i0 = tile_base + idx0;
@@ -346,8 +369,8 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         for (int j = 0; j < kPItems; ++j) {
             if (st[j] & kLive) {
                 const u32 b = cdf_pos_plain(key[j], sm.tab, xmax) >> 16;
-                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] & kPayloadFg) ? 0x10000u : 0u));
-                st[j] |= (b << 16) | (old & 0xffffu);
+                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] >> 31) << 16));
+                st[j] |= (b << kPB) | (old & 0xffffu);
             }
         }
     } else {
@@ -355,8 +378,8 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         for (int j = 0; j < kPItems; ++j) {
             if (st[j] & kLive) {
                 const u32 b = cdf_pos_ties(key[j], i0 + 32 * j, n, sm.tab, tie, xmax) >> 16;
-                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] & kPayloadFg) ? 0x10000u : 0u));
-                st[j] |= (b << 16) | (old & 0xffffu);
+                const u32 old = atomicAdd(&sm_cnt[b], 1u | ((st[j] >> 31) << 16));
+                st[j] |= (b << kPB) | (old & 0xffffu);
             }
         }
     }
@@ -397,9 +420,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 #pragma unroll
     for (int j = 0; j < kPItems; ++j)
         if (st[j] & kLive)
-            // payload while in shared memory: {fg, neg, bucket:12..22, position in the tile:0..11}
-            sm.exch[sm_pre[(st[j] >> 16) & 0x7ffu] + (st[j] & 0x1fffu)] =
-                ((u64)key[j] << 32) | (st[j] & (kPayloadFg | kPayloadNeg)) | (((st[j] >> 16) & 0x7ffu) << 12) | (idx0 + 32 * j);
+            // payload while in shared memory: {fg, neg, bucket:P..P+10, position in the tile:0..P-1}
+            sm.exch[sm_pre[(st[j] >> kPB) & 0x7ffu] + (st[j] & kPosMask)] =
+                ((u64)key[j] << 32) | (st[j] & (kPayloadFg | kPayloadNeg | (0x7ffu << kPB))) | (idx0 + 32 * j);
 
     bool overflow = false;
 #pragma unroll
@@ -434,9 +457,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         if (pos < total) {
             const u64 v = sm.exch[pos];
             const u32 pl = (u32)v;
-            const u32 d = sm_cnt[(pl >> 12) & 0x7ffu];
+            const u32 d = sm_cnt[(pl >> kPB) & 0x7ffu];
             // global payload: {fg, neg, pixel index in the segment}
-            if (d != kNoDst) dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & 0xfffu));
+            if (d != kNoDst) dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & kPosMask));
         }
     }
     }
@@ -466,8 +489,7 @@ struct LocalShared {
     unsigned short wpre[kCntWords];      // elements in lower words of the same warp chunk
     unsigned short where[kBTile];        // [first rank of a shared slot + ticket] -> index into stage
     u32 col[kColMax];                    // elements sharing a slot: {first rank:0..12, ticket:13..20, count:21..28} -> rank
-    u32 fgbits[kBTile / 32];             // bit r: the element of local rank r is foreground
-    u32 fgpre[kBTile / 32];
+    uint2 fg[kBTile / 32];               // .x bit r: the element of local rank 32 * i + r is foreground; .y: foreground elements of lower words
     u32 scan_tmp[kBWarps];
     u32 woff[kBWarps];
     u64 red64[kBWarps];
@@ -512,7 +534,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
     constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // phase A: one atomic per element; {fine slot:0..14, ticket:16..23}
+    // phase A: one atomic per element; {fine slot:0..14, foreground:15, ticket:16..23}
     bool over = false;
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
@@ -526,7 +548,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
             const u32 sh = (f % FW) * W;
             const u32 t = (atomicAdd(&sm.cntw[f / FW], 1u << sh) >> sh) & FM;
             over |= t == FM;                         // the field was already full: this add spilled into the next one
-            rk[j] = f | (t << 16);
+            rk[j] = f | (((u32)e >> 31) << 15) | (t << 16);
         }
     }
     if (__syncthreads_or(over)) return false;
@@ -574,14 +596,14 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
         const u32 idx = j * kBThreads + tid;
         if (j * kBThreads >= cnt) break;
         if (idx < cnt) {
-            const u32 f = rk[j] & 0xffffu, t = rk[j] >> 16;
+            const u32 f = rk[j] & 0x7fffu, t = rk[j] >> 16, fg = rk[j] & 0x8000u;
             const u32 wi = f / FW, sh = (f % FW) * W;
             const u32 word = sm.cntw[wi];
             const u32 c = (word >> sh) & FM;
             const u32 first = (u32)sm.wpre[wi] + sm.woff[wi / (kCntWords / kBWarps)] + field_sum<W>(word & ((1u << sh) - 1u));
             rk[j] = first | (t << 13) | (c << 21);
             if (c == 1) {
-                if ((u32)sm.stage[idx] & kPayloadFg) atomicOr(&sm.fgbits[first >> 5], 1u << (first & 31u));
+                if (fg) atomicOr(&sm.fg[first >> 5].x, 1u << (first & 31u));
             } else {
                 sm.where[first + t] = (unsigned short)idx;
                 const u32 q = atomicAdd(&sm.ncol, 1u);          // dense list: phase C runs without idle lanes
@@ -603,7 +625,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
         u32 pred = 0;
         for (u32 m = 0; m < c; ++m) pred += ((sm.stage[sm.where[first + m]] & cmp_mask) < ce) ? 1u : 0u;
         const u32 r = first + pred;
-        if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
+        if ((u32)e & kPayloadFg) atomicOr(&sm.fg[r >> 5].x, 1u << (r & 31u));
         sm.col[i] = r;
     }
     if (ncol_all > (u32)kColMax) {                    // list full (heavy ties): the rest in place, lanes idle
@@ -618,7 +640,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
                 u32 pred = 0;
                 for (u32 m = 0; m < c; ++m) pred += ((sm.stage[sm.where[first + m]] & cmp_mask) < ce) ? 1u : 0u;
                 const u32 r = first + pred;
-                if ((u32)e & kPayloadFg) atomicOr(&sm.fgbits[r >> 5], 1u << (r & 31u));
+                if ((u32)e & kPayloadFg) atomicOr(&sm.fg[r >> 5].x, 1u << (r & 31u));
                 rk[j] = r;
             }
         }
@@ -634,7 +656,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
 
 __device__ __forceinline__ void local_reset(LocalShared &sm) {
     for (u32 i = threadIdx.x; i < (u32)kCntWords; i += kBThreads) sm.cntw[i] = 0;
-    if (threadIdx.x < kBTile / 32) sm.fgbits[threadIdx.x] = 0;
+    if (threadIdx.x < kBTile / 32) sm.fg[threadIdx.x].x = 0;
     if (threadIdx.x == 0) sm.ncol = 0;
 }
 
@@ -665,7 +687,7 @@ __device__ __noinline__ void local_sort_all(LocalShared &sm, u32 cnt) {
     for (u32 q = tid; q < N; q += kBThreads) {       // N is a multiple of 32: whole warps
         const bool fg = q < cnt && ((u32)sm.stage[q] & kPayloadFg);
         const u32 m = __ballot_sync(RTDA_FULL_MASK, fg);
-        if (lane == 0) sm.fgbits[q >> 5] = m;
+        if (lane == 0) sm.fg[q >> 5].x = m;
     }
     __syncthreads();
 }
@@ -729,9 +751,9 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     }
     const u32 base_cnt = (u32)sm.base, base_fg = (u32)(sm.base >> 32);
     {
-        const u32 v = tid < kBTile / 32 ? (u32)__popc(sm.fgbits[tid]) : 0u;
+        const u32 v = tid < kBTile / 32 ? (u32)__popc(sm.fg[tid].x) : 0u;
         const u32 e = block_excl_scan<kBWarps, u32>(v, sm.scan_tmp, nullptr);
-        if (tid < kBTile / 32) sm.fgpre[tid] = e;
+        if (tid < kBTile / 32) sm.fg[tid].y = e;
     }
     __syncthreads();
 
@@ -747,7 +769,8 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const u32 pay = (u32)e;
             const u32 lr = rk[j];
             const u32 r = base_cnt + lr;                                  // 0-based rank in the sorted segment
-            const u32 f_ex = base_fg + sm.fgpre[lr >> 5] + (u32)__popc(sm.fgbits[lr >> 5] & ((1u << (lr & 31u)) - 1u));
+            const uint2 fw = sm.fg[lr >> 5];
+            const u32 f_ex = base_fg + fw.y + (u32)__popc(fw.x & ((1u << (lr & 31u)) - 1u));
             const u32 f_in = f_ex + (pay >> 31);
             const float jac = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_in), __uint2float_rn(G + r + 1u - f_in)));
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
