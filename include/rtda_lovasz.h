@@ -161,7 +161,7 @@ int rtda_confusion_argmax_accumulate(const float *logits, const void *labels, in
  * last read into the caller's host arrays, and recycles the events.  Off by
  * default; meant for single-threaded benchmark use (the event list is global).
  * Stages: see rtda_profile_stage_name(0 .. RTDA_PROFILE_STAGES-1). */
-#define RTDA_PROFILE_STAGES 16
+#define RTDA_PROFILE_STAGES 17
 int rtda_profile_enable(int on);
 int rtda_profile_read(double *stage_ms_host, int64_t *stage_launches_host, int n_stages);
 const char *rtda_profile_stage_name(int stage);

@@ -40,7 +40,7 @@ SIGNATURES = {
     "rtda_profile_stage_name": (ctypes.c_char_p, [_int]),
 }
 
-PROFILE_STAGES = 16
+PROFILE_STAGES = 17
 
 
 def profile_enable(on: bool) -> None:

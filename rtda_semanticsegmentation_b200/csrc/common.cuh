@@ -26,7 +26,7 @@ namespace rtda {
 enum Stage {
     kStageMemset = 0, kStagePrep, kStageScan, kStagePass0, kStagePass1, kStagePass2, kStageRankLast,
     kStageFinalize, kStageBwd, kStageConfusion, kStageConfusionArgmax, kStageOther,
-    kStageSplit, kStagePart, kStageLocal, kStageHistFb
+    kStageSplit, kStagePart, kStageLocal, kStageHistFb, kStagePlan
 };
 bool profile_enabled();
 void profile_begin(int stage, cudaStream_t st);

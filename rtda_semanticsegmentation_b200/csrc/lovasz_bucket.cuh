@@ -229,7 +229,7 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     }
     // cumulative map with a floor of 1/kPrior sample per bin: a bin the sample missed still gets a
     // little width, so the elements that do fall there spread over slots instead of piling into one
-    u32 *tab = table + (size_t)seg * (kTabBins + 1);
+    u32 *tab = table + (size_t)seg * kTabStride;
     u32 *tie = ties + (size_t)seg * kTabBins;
     const u64 scale = (u64)NB << 16;
     const u64 denom = (u64)kPrior * m_nz + kTabBins;
@@ -255,11 +255,32 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     if (tid == 0) { tab[kTabBins] = (u32)scale; nb_out[seg] = NB | (seg_ties ? kNbTies : 0u); }
 }
 
+// mbarrier + bulk asynchronous copy (cp.async.bulk, the 1-D TMA path): one thread starts the copy,
+// the data arrives in shared memory without passing through registers, every reader waits on the barrier.
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // ---------------------------------------------------------------------------
 // k_part: level 1.  One block per (segment, tile of kPTile pixels), segment-major.
 struct PartShared {
     u64 exch[kPTile];
     u32 tab[kTabBins + 4];
+    u64 mbar;
     u32 scan_tmp[kPWarps];
     u32 skip;
     u32 arrays[1];       // cnt[nbk_pad] (count | fg << 16, then the global destination), pre[nbk_pad]
@@ -283,7 +304,14 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 seg = blockIdx.x / bps;
     const u32 tile0 = (blockIdx.x - seg * bps) * kPTilesPerBlock;
     // other blocks of this kernel may raise the flag while this one starts: one thread decides for the block
-    if (tid == 0) sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
+    if (tid == 0) {
+        sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
+        mbar_init(&sm.mbar, 1);
+        // the segment's map (16 KB) comes in by one bulk copy; it is first needed after the tile's own
+        // loads have returned, so its latency is hidden behind them (a register-staged copy stalled
+        // every block for a full round trip to L2: 12 % of this kernel's stall samples)
+        if (!sm.skip) bulk_load(sm.tab, table + (size_t)seg * kTabStride, kTabStride * (u32)sizeof(u32), &sm.mbar);
+    }
     __syncthreads();
     if (sm.skip) return;
     const u32 nb_raw = nb[seg];
@@ -295,15 +323,11 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 n = (u32)geo.n;
     const size_t seg_off = (size_t)seg * n;
     const u32 *tie = ties + (size_t)seg * kTabBins;         // read through L1: touched only for flagged intervals
-    {
-        const u32 *tsrc = table + (size_t)seg * (kTabBins + 1);
-        for (u32 k = tid; k < (u32)kTabBins + 1u; k += kPThreads) sm.tab[k] = tsrc[k];
-    }
     for (u32 tile = tile0; tile < tile0 + kPTilesPerBlock; ++tile) {
     const u32 tile_base = tile * (u32)kPTile;
     if (tile_base >= n) break;
     const u32 count = (n - tile_base < (u32)kPTile) ? n - tile_base : (u32)kPTile;
-    __syncthreads();          // the previous tile no longer uses the shared arrays (and the map is loaded)
+    __syncthreads();          // the previous tile no longer uses the shared arrays
 
     // per element: the key and one word of state {fg:31, neg:30, live:29, bucket:P..P+10, rank in (tile, bucket):0..P-1}
     // with P = kPPosBits (a rank is below the tile size) - the layout of the exchanged payload, so that
@@ -363,6 +387,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         }
     }
     __syncthreads();
+    if (tile == tile0) mbar_wait(&sm.mbar, 0);       // the map has arrived (block-uniform; later tiles find it there)
 
     if (!has_ties) {                                 // block-uniform: the common case keeps the short map
 #pragma unroll
@@ -492,31 +517,10 @@ struct LocalShared {
     uint2 fg[kBTile / 32];               // .x bit r: the element of local rank 32 * i + r is foreground; .y: foreground elements of lower words
     u32 scan_tmp[kBWarps];
     u32 woff[kBWarps];
-    u64 red64[kBWarps];
     long long red[2][kBWarps];
     u64 mbar;
-    u64 base;
     u32 ncol;
-    u32 skip;
 };
-
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    u32 ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
 
 template <int W>
 __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields of w
@@ -526,9 +530,12 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 
 // One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
 // rk[j] ends as the local rank of element j * kBThreads + tid.
+struct LinMap { u32 lo, R, sh, M; };             // in-bucket linear map (k_plan); R = 0xFFFFFFFF: use the segment's map
 template <int W>
 __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
-                                            bool has_ties, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
+                                            bool has_ties, const LinMap lm, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
+    const u32 lin_lo = lm.lo, lin_R = lm.R, lin_sh = lm.sh, lin_M = lm.M;
+    const bool lin = lin_R != 0xFFFFFFFFu;           // block-uniform
     constexpr u32 FW = 32 / W;                       // fields per word
     constexpr u32 FM = (1u << W) - 1u;               // largest field value
     constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
@@ -544,7 +551,18 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
         if (idx < cnt) {
             // the keys of one bucket share a few table entries: the loads broadcast out of L1
             const u64 e = sm.stage[idx];
-            const u32 f = (cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu) >> FSHIFT;
+            u32 x16;
+            if (lin) {
+                // any monotone map of the key orders the bucket; where the segment's map is close to one
+                // straight line over the bucket's key range, that line needs no table lookups
+                const u32 tau = tau_of((u32)(e >> 32));
+                u32 d = (tau > lin_lo ? tau : lin_lo) - lin_lo;
+                d = d < lin_R ? d : lin_R;
+                x16 = __umulhi(d << lin_sh, lin_M);
+            } else {
+                x16 = cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu;
+            }
+            const u32 f = x16 >> FSHIFT;
             const u32 sh = (f % FW) * W;
             const u32 t = (atomicAdd(&sm.cntw[f / FW], 1u << sh) >> sh) & FM;
             over |= t == FM;                         // the field was already full: this add spilled into the next one
@@ -692,56 +710,155 @@ __device__ __noinline__ void local_sort_all(LocalShared &sm, u32 cnt) {
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------
+// k_plan: between the two levels, one block per segment.  Everything a level-2 block needs to know
+// before it can start is worked out once here and handed over in ONE 32-byte record per bucket, so a
+// k_local block begins with a single round trip to L2 instead of a chain of dependent loads (with two
+// blocks per SM and ~17 us per block, every microsecond of start-up latency is 6 % of the kernel):
+//   a = {elements, elements in earlier buckets, foreground elements in earlier buckets, flags}
+//   b = {tau_lo, R, shift, multiplier} of the in-bucket linear map (flag kPlanLin)
+// The linear map: any monotone function of the key orders a bucket.  Inverting the segment's map at
+// the bucket's two ends gives its key range [tau_lo, tau_lo + R]; where the map's slope varies by less
+// than RTDA_LOCAL_LINEAR x over the intervals the bucket spans, a straight line over that range
+// spreads the elements over the fine slots about as evenly as the map itself and needs no table
+// lookups in k_local (their L1 latency was the largest single stall there).
+constexpr u32 kPlanLive = 1u, kPlanTies = 2u, kPlanLin = 4u;
+// grid (S, ceil(NBK / kPlanThreads)): one thread per bucket, so the searches of a segment run side by side
+__global__ void __launch_bounds__(kPlanThreads)
+k_plan(Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb, const u32 *__restrict__ table,
+       const u64 *__restrict__ cursor, const u32 *__restrict__ fb_flag, uint4 *__restrict__ plan) {
+    __shared__ __align__(16) u32 tab[kTabStride];
+    __shared__ u64 scan_tmp[kPlanThreads / 32];
+    __shared__ u64 mbar;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 seg = blockIdx.x;
+    const u32 NBK = (u32)geo.NBK;
+    const u32 b0 = blockIdx.y * (u32)kPlanThreads;                  // this block's buckets: [b0, b0 + kPlanThreads)
+    const u32 b = b0 + tid;
+    uint4 *out = plan + (size_t)seg * NBK * 2;
+    const u32 nb_raw = nb[seg];
+    const u32 NB = nb_raw & ~kNbTies;
+    const bool has_ties = (nb_raw & kNbTies) != 0u;
+    if (seg_fg[seg] == 0 || fb_flag[seg] != 0 || NB == 0) {          // nothing for level 2 in this segment
+        if (b < NBK) out[2 * b] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const bool want_map = !has_ties && RTDA_LOCAL_LINEAR != 0;
+    if (tid == 0 && want_map) {                                      // the map arrives while the cursors are summed
+        mbar_init(&mbar, 1);
+        bulk_load(tab, table + (size_t)seg * kTabStride, kTabStride * (u32)sizeof(u32), &mbar);
+    }
+    // elements (low word) and foreground elements (high word) of the buckets before this one
+    const u64 *cur = cursor + (size_t)seg * NBK;
+    const u64 c = b < NB ? cur[b] : 0ull;
+    u64 before = 0;
+    for (u32 i = tid; i < b0 && i < NB; i += kPlanThreads) before += cur[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(RTDA_FULL_MASK, before, o);
+    u64 total_before;
+    {
+        if (lane == 0) scan_tmp[tid >> 5] = before;
+        __syncthreads();
+        u64 t = 0;
+#pragma unroll
+        for (int w = 0; w < kPlanThreads / 32; ++w) t += scan_tmp[w];
+        total_before = t;
+        __syncthreads();
+    }
+    const u64 run = total_before + block_excl_scan<kPlanThreads / 32, u64>(c, scan_tmp, nullptr);   // (barriers: mbar is initialised)
+    if (b >= NBK) return;                                            // (after the last barrier)
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
+    const u32 cnt = (u32)c;
+    // cnt > kBTile: the region overflowed in k_part, the segment's flag is already raised
+    if (b < NB && cnt != 0u && cnt <= (u32)kBTile) a = make_uint4(cnt, (u32)run, (u32)(run >> 32), kPlanLive | (has_ties ? kPlanTies : 0u));
+    if (want_map) mbar_wait(&mbar, 0);
+    if (a.w && want_map) {
+        // interval p with tab[p] <= X < tab[p + 1] at both ends of the bucket (tab[0] = 0, tab[kTabBins] = NB << 16 > X)
+        u32 pe[2], te[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const u32 X = e ? (((b + 1u) << 16) - 1u) : (b << 16);
+            u32 p = 0;
+#pragma unroll
+            for (u32 step = kTabBins / 2; step >= 1u; step >>= 1)
+                if (p + step <= (u32)kTabBins - 1u && tab[p + step] <= X) p += step;
+            const u32 tp = tab[p], dx = tab[p + 1u] - tp;           // dx >= 1
+            const u64 num = (u64)(X - tp) << 19;
+            // lower end: floor, never above the bucket's smallest tau; upper end: ceil, never below its largest
+            u32 off = e ? (u32)((num + dx - 1u) / dx) + 1u : (u32)(num / dx);
+            off = off < 0x7FFFFu ? off : 0x7FFFFu;
+            pe[e] = p;
+            te[e] = (p << 19) + off;
+        }
+        const u32 span = pe[1] - pe[0] + 1u;
+        if (span <= 32u && te[1] >= te[0]) {
+            u32 dmin = 0xFFFFFFFFu, dmax = 0u;
+            for (u32 q = pe[0]; q <= pe[1]; ++q) {
+                const u32 dd = tab[q + 1u] - tab[q];
+                dmin = dd < dmin ? dd : dmin;
+                dmax = dd > dmax ? dd : dmax;
+            }
+            if (dmin != 0u && dmax <= (u64)RTDA_LOCAL_LINEAR * dmin) {
+                const u32 R = te[1] - te[0], Rn = R ? R : 1u;
+                const u32 sh = (u32)__clz(Rn);
+                l = make_uint4(te[0], R, sh, (u32)((65535ull << 32) / ((u64)Rn << sh)));   // (Rn << sh) in [2^31, 2^32)
+                a.w |= kPlanLin;
+            }
+        }
+    }
+    out[2 * b] = a;
+    out[2 * b + 1] = l;
+}
+
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
-        const u32 *__restrict__ table, const u32 *__restrict__ ties, const u64 *__restrict__ cursor,
-        u32 *__restrict__ fb_flag, u32 *__restrict__ fb_any, unsigned long long *__restrict__ seg_sum,
-        float *__restrict__ unit_grad) {
+        const u32 *__restrict__ table, const u32 *__restrict__ ties, const uint4 *__restrict__ plan,
+        unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad) {
     extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 seg = blockIdx.x / (u32)geo.NBK;
     const u32 b = blockIdx.x - seg * (u32)geo.NBK;
+    // k_plan's record for this bucket: one round trip decides whether the block runs and tells it how
+    // (all four loads are issued before the first of them is looked at)
+    const uint4 pa = plan[2 * (size_t)blockIdx.x];
+    const uint4 pl = plan[2 * (size_t)blockIdx.x + 1];
     const u32 G = seg_fg[seg];
-    if (tid == 0) {
-        sm.skip = (G == 0 || ld_relaxed(fb_flag + seg) != 0 || b >= (nb[seg] & ~kNbTies)) ? 1u : 0u;
-        mbar_init(&sm.mbar, 1);
-    }
-    __syncthreads();
-    if (sm.skip) return;
-    const u64 *cur = cursor + (size_t)seg * geo.NBK;
-    const u32 cnt = (u32)cur[b];
-    if (cnt > (u32)kBTile) return;                 // overflowed in k_part (flag already raised)
-    if (cnt == 0) return;
-    // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
-    if (tid == 0) bulk_load(sm.stage, regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile, ((cnt + 1u) & ~1u) * 8u, &sm.mbar);
     const u32 nb_raw = nb[seg];
-    const bool has_ties = (nb_raw & kNbTies) != 0u;
-    const u32 xmax = ((nb_raw & ~kNbTies) << 16) - 1u;
-    const u32 *tab = table + (size_t)seg * (kTabBins + 1);
-    const u32 *tie = ties + (size_t)seg * kTabBins;
-
-    // meanwhile: elements (low word) and foreground elements (high word) of the earlier buckets
-    u64 acc64 = 0;
-    for (u32 i = tid; i < b; i += kBThreads) acc64 += cur[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc64 += __shfl_xor_sync(RTDA_FULL_MASK, acc64, o);
-    if (lane == 0) sm.red64[warp] = acc64;
-    local_reset(sm);
-    __syncthreads();
+    if (!(pa.w & kPlanLive)) return;
+    const u32 cnt = pa.x;
     if (tid == 0) {
-        u64 t = 0;
-#pragma unroll
-        for (int w = 0; w < kBWarps; ++w) t += sm.red64[w];
-        sm.base = t;
+        mbar_init(&sm.mbar, 1);
+        // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
+        bulk_load(sm.stage, regions + ((size_t)seg * geo.NBK + b) * (size_t)kBTile, ((cnt + 1u) & ~1u) * 8u, &sm.mbar);
     }
+#if RTDA_LOCAL_PREFETCH > 0
+    // hint: blocks start in index order; the bucket of the block RTDA_LOCAL_PREFETCH places ahead is asked
+    // into L2 now, so that block's bulk copy does not wait for DRAM
+    if (tid == 32) {
+        const size_t pb = (size_t)blockIdx.x + RTDA_LOCAL_PREFETCH;
+        if (pb < (size_t)gridDim.x) {
+            const uint4 fa = plan[2 * pb];
+            if (fa.w & kPlanLive)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(regions + pb * (size_t)kBTile), "r"(((fa.x + 1u) & ~1u) * 8u) : "memory");
+        }
+    }
+#endif
+    const bool has_ties = (pa.w & kPlanTies) != 0u;
+    const u32 xmax = ((nb_raw & ~kNbTies) << 16) - 1u;
+    const u32 *tab = table + (size_t)seg * kTabStride;
+    const u32 *tie = ties + (size_t)seg * kTabBins;
+    const u32 base_cnt = pa.y, base_fg = pa.z;
+    const LinMap lm = {pl.x, (pa.w & kPlanLin) ? pl.y : 0xFFFFFFFFu, pl.z, pl.w};
+    local_reset(sm);
+    __syncthreads();                               // the barrier is initialised, the counters are zero
     mbar_wait(&sm.mbar, 0);
 
     u32 rk[kBItems];
-    if (!local_ranks<4>(sm, tab, tie, has_ties, (u32)geo.n, cnt, xmax, rk)) {
+    if (!local_ranks<4>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8>(sm, tab, tie, has_ties, (u32)geo.n, cnt, xmax, rk)) {
+        if (!local_ranks<8>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
             // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
             // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
             local_sort_all(sm, cnt);
@@ -749,7 +866,6 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             for (int j = 0; j < kBItems; ++j) rk[j] = j * kBThreads + tid;
         }
     }
-    const u32 base_cnt = (u32)sm.base, base_fg = (u32)(sm.base >> 32);
     {
         const u32 v = tid < kBTile / 32 ? (u32)__popc(sm.fg[tid].x) : 0u;
         const u32 e = block_excl_scan<kBWarps, u32>(v, sm.scan_tmp, nullptr);

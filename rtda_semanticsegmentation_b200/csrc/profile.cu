@@ -71,7 +71,7 @@ extern "C" const char *rtda_profile_stage_name(int stage) {
     static const char *names[RTDA_PROFILE_STAGES] = {
         "memset_workspace", "k_prep", "k_scan", "k_sort_pass<0,probas>", "k_sort_pass<1>", "k_sort_pass<2>",
         "k_rank_last", "k_finalize", "k_bwd", "k_confusion", "k_confusion_argmax", "gaps_between_launches",
-        "k_split", "k_part", "k_local", "k_hist_fb"};
+        "k_split", "k_part", "k_local", "k_hist_fb", "k_plan"};
     if (stage < 0 || stage >= RTDA_PROFILE_STAGES) return "?";
     return names[stage];
 }
