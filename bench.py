@@ -553,6 +553,7 @@ def main():
         "k_prep": px_step * (8 + 1),                       # labels in, class codes out
         "k_split": E // 16 * 8,                            # 1/16 sample, half of every 32-byte sector used
         "k_part": E * 4 + E * 1 + E * 8,                   # probabilities + codes (re-read per class) in, pairs out
+        "k_plan": None,
         "k_local": E * 8 + E * 4,                          # pairs in, 4-byte gradient scatter out
         "k_hist_fb": None,
         "k_scan": None,
