@@ -291,18 +291,20 @@ static inline size_t part_smem_bytes(int nbk) {
     return sizeof(PartShared) + 2 * pad * sizeof(u32);
 }
 
+template <int TPB>                                  // consecutive tiles of one segment per block (part_tiles_per_block)
 __global__ void __launch_bounds__(kPThreads, kPBlocksPerSM)
 k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
        const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ ties,
        const u32 *__restrict__ nb, u64 *__restrict__ cursor, u64 *__restrict__ out, u32 *__restrict__ fb_flag,
        u32 *__restrict__ fb_any, float *__restrict__ unit_grad) {
+    constexpr u32 tpb = (u32)TPB;
     extern __shared__ __align__(16) unsigned char part_smem[];
     PartShared &sm = *reinterpret_cast<PartShared *>(part_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // a block takes kPTilesPerBlock consecutive tiles of one segment: the map is loaded once for them
-    const u32 bps = ((u32)geo.T1 + kPTilesPerBlock - 1) / kPTilesPerBlock;
+    // a block takes tpb consecutive tiles of one segment (part_tiles_per_block): the map is loaded once for them
+    const u32 bps = ((u32)geo.T1 + tpb - 1u) / tpb;
     const u32 seg = blockIdx.x / bps;
-    const u32 tile0 = (blockIdx.x - seg * bps) * kPTilesPerBlock;
+    const u32 tile0 = (blockIdx.x - seg * bps) * tpb;
     // other blocks of this kernel may raise the flag while this one starts: one thread decides for the block
     if (tid == 0) {
         sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
@@ -323,7 +325,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 n = (u32)geo.n;
     const size_t seg_off = (size_t)seg * n;
     const u32 *tie = ties + (size_t)seg * kTabBins;         // read through L1: touched only for flagged intervals
-    for (u32 tile = tile0; tile < tile0 + kPTilesPerBlock; ++tile) {
+    for (u32 tile = tile0; tile < tile0 + tpb; ++tile) {
     const u32 tile_base = tile * (u32)kPTile;
     if (tile_base >= n) break;
     const u32 count = (n - tile_base < (u32)kPTile) ? n - tile_base : (u32)kPTile;
