@@ -564,6 +564,11 @@ def main():
         "k_finalize": None,
         "k_bwd": E * 8,
     }
+    fb_segments = int(rtda.segment_sort_paths((imgs, C, H, W), per_image).sum())
+    if fb_segments == 0:
+        # no segment fell back: the LSD kernels were launched and exited at once, they moved no data
+        for name in ("k_sort_pass<0,probas>", "k_sort_pass<1>", "k_sort_pass<2>", "k_rank_last"):
+            own_bytes[name] = None
     kernels = []
     launches = 0
     for name, (ms, cnt) in stages.items():
@@ -593,7 +598,7 @@ def main():
             "labels": "int64", "launch": ("cuda_graph replay of the public fwd+bwd call (one graph per input set)" + ("" if world == 1 else " on this rank's images, then one asynchronous all-reduce of the packed partials per step")) if graphs is not None else "eager",
             "l2_policy": f"{n_sets} distinct input sets ({n_sets * set_bytes >> 20} MiB > 126 MiB L2) rotated every step",
             "loss": loss_value, "sort_path": args.sort_path,
-            "segments_sorted_by_lsd_fallback": int(rtda.segment_sort_paths((imgs, C, H, W), per_image).sum()),
+            "segments_sorted_by_lsd_fallback": fb_segments,
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": e2e_ms,
