@@ -5,22 +5,26 @@
 // shared memory four times.  For the smooth key distributions softmax outputs have, a sample of the
 // keys predicts the distribution well enough to finish in two movements:
 //
-//   k_split   one block per segment (group, class): 11-bit-prefix histogram of a 1/16 sample of the
+//   k_split   a few blocks per segment (group, class): 12-bit-prefix histogram of a 1/16 sample of the
 //             segment's keys -> a monotone piecewise-linear map key -> bucket with equal expected
 //             occupancy (kBMean elements per bucket).
 //   k_part    level 1: every element goes to its bucket's fixed-capacity region (kBTile slots) through
 //             a shared-memory exchange, one global cursor claim per (tile, bucket).  Unordered inside
 //             a bucket: level 2 orders by (key, pixel index) explicitly, so no stability is needed and
-//             there is no look-back chain.
-//   k_local   level 2: one block per bucket.  Interpolation sort in shared memory: slot =
-//             (key - min) * count / (max - min + 1), one atomic per element, a scan, one placement;
-//             elements sharing a slot (about one neighbour on average) are ordered by direct
-//             comparison.  rank = elements in earlier buckets + local rank, likewise the foreground
-//             rank; lovasz_grad, the dot product and the gradient scatter follow as in k_rank_last.
+//             there is no look-back chain.  The segment's map comes in by one bulk copy (TMA 1-D).
+//   k_plan    one thread per bucket: a 32-byte record {count, elements and foreground elements of the
+//             earlier buckets, flags; in-bucket linear key map} so that a level-2 block starts after a
+//             single round trip to L2.
+//   k_local   level 2: one block per bucket, staged in shared memory by one bulk copy.  Interpolation
+//             sort: fine slot = monotone function of the key (the straight line of k_plan, else the
+//             segment's map), one atomic on packed counters per element, a scan, one placement;
+//             elements sharing a slot (about 15 %) are ordered by direct comparison.  rank = elements
+//             in earlier buckets + local rank, likewise the foreground rank; lovasz_grad, the dot
+//             product and the gradient scatter follow as in k_rank_last.
 //
 // The order produced is exactly the LSD path's: ascending key (= descending error), ties by ascending
 // pixel index, so both paths are bit-identical.  Anything the map cannot handle - a bucket that
-// overflows its region, a slot chain longer than kChainMax (massive exact ties), more buckets than
+// overflows its region (a massive exact tie that is not on an interval boundary), more buckets than
 // kBMaxBuckets - raises the segment's fallback flag on the device and the LSD kernels, which always
 // run behind (persistent grids that exit at once when no flag is set), redo that segment.  No host
 // synchronisation is involved.
