@@ -39,6 +39,17 @@ def test_version_and_error_strings(lib):
         assert lib.rtda_error_string(code).startswith(b"rtda:")
 
 
+def test_profile_stage_table_matches_the_header(lib):
+    # the Python reader sizes its arrays with PROFILE_STAGES; the library rejects a smaller count
+    n = int(re.search(r"#define\s+RTDA_PROFILE_STAGES\s+(\d+)", open(_lib.HEADER).read()).group(1))
+    assert _lib.PROFILE_STAGES == n
+    names = [lib.rtda_profile_stage_name(i).decode() for i in range(n)]
+    assert len(set(names)) == n and "?" not in names
+    for k in ("k_prep", "k_split", "k_part", "k_plan", "k_local", "k_finalize", "k_bwd", "k_confusion"):
+        assert k in names
+    assert lib.rtda_profile_stage_name(n) == b"?"
+
+
 def test_workspace_query_and_argument_errors(lib):
     n = ctypes.c_size_t(0)
     assert lib.rtda_lovasz_workspace_bytes(4, 19, 512 * 1024, 0, ctypes.byref(n)) == 0
