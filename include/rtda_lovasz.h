@@ -19,7 +19,8 @@
  *     the caller, all work is enqueued on `stream` (a cudaStream_t passed as
  *     void*), so the calls are re-entrant per (device, stream);
  *   - all pointers are DEVICE pointers unless the name ends in _host;
- *   - probabilities / gradients are fp32 NCHW contiguous, 16-byte aligned.
+ *   - probabilities / gradients are fp32 NCHW contiguous; 16-byte aligned when HW % 4 == 0
+ *     (the float4 paths), 4-byte aligned otherwise (so a batch slice of an odd-sized map works).
  *
  * Label element types (`label_kind`): RTDA_LABEL_I64 is what the reference's
  * callers pass (`labels.long()`, train_lovasz.py:66); U8 / I32 are fast paths
@@ -35,12 +36,12 @@
 extern "C" {
 #endif
 
-#define RTDA_ABI_VERSION 1
+#define RTDA_ABI_VERSION 2
 
 #define RTDA_E_ARG (-1)        /* null pointer / non-positive size */
 #define RTDA_E_RANGE (-2)      /* a size exceeds what the kernels index (see below) */
 #define RTDA_E_WORKSPACE (-3)  /* ws_bytes smaller than rtda_lovasz_workspace_bytes */
-#define RTDA_E_ALIGN (-4)      /* a pointer is not 16-byte aligned */
+#define RTDA_E_ALIGN (-4)      /* a pointer is not aligned as the conventions above require */
 
 #define RTDA_LABEL_I64 0
 #define RTDA_LABEL_U8 1
@@ -90,7 +91,7 @@ int rtda_lovasz_set_sort_path(int path);
  *                 group)/d(probas) for grad_out = 1 before the 1/K and 1/G factors,
  *                 i.e. -g_rank * sgn(fg - p); rows of absent classes and ignored pixels
  *                 are NOT written.  May be NULL (loss only, e.g. under torch.no_grad()).
- *   codes         [B*HW] u8, 4-byte aligned: the class of every pixel, 255 = ignored or
+ *   codes         [B*HW] u8, 4-byte aligned when HW % 4 == 0: the class of every pixel, 255 = ignored or
  *                 out of range; required with unit_grad (the backward reads both), else
  *                 may be NULL.
  *   loss          [1]    fp32  the scalar loss (0 when nothing is valid)
@@ -99,9 +100,15 @@ int rtda_lovasz_set_sort_path(int path);
  *   n_present     [G]    i32   K of each group
  *   group_loss    [G]    fp32  loss of each group (image); may be NULL
  *   label_errors  [1]    i32   number of labels outside [0,C) and != ignore; may be NULL
- *   packed        [2+2C] f64   partials for a batch sharded over ranks (per_image): {sum of group
- *                 losses, G, per-class sums of class_loss, per-class sums of class_present};
- *                 one all-reduce(sum) of this buffer gives the global mean; may be NULL
+ *   packed        [4+2C] f64   partials for a batch sharded over ranks (per_image): {sum of group
+ *                 losses, G, per-class sums of class_loss, per-class sums of class_present,
+ *                 sum of -log p_label over the valid pixels, number of valid pixels} (the last two
+ *                 are 0 from rtda_lovasz_fwd and filled by rtda_hybrid_fwd); one all-reduce(sum) of
+ *                 this buffer gives the global means; may be NULL
+ *
+ * Non-finite probabilities: a NaN (or an infinite) error among the sorted elements of a class makes
+ * that class's loss NaN (or +inf) and the means carry it into `loss`, as torch.dot does in the
+ * reference (lovasz_loss.py:180).  The gradient at such elements is unspecified (finite).
  */
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("RTDA_LIB_PATH") or os.path.join(_PKG, "librtda_lovasz
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "rtda_lovasz.h")
 
 LABEL_I64, LABEL_U8, LABEL_I32 = 0, 1, 2
+ABI_VERSION = 2   # RTDA_ABI_VERSION of include/rtda_lovasz.h
 
 # name -> (restype, argtypes); must list every function include/rtda_lovasz.h declares
 _vp, _i64, _int, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
@@ -90,8 +91,8 @@ def load():
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.rtda_version() != 1:
-        raise NativeLibraryError(f"ABI version mismatch: library {lib.rtda_version()}, binding 1")
+    if lib.rtda_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.rtda_version()}, binding {ABI_VERSION}; rebuild it")
     _lib = lib
     return lib
 

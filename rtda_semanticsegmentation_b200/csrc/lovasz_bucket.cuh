@@ -819,7 +819,7 @@ k_plan(Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb, con
 __global__ void __launch_bounds__(kBThreads, 2)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u32 *__restrict__ ties, const uint4 *__restrict__ plan,
-        unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad) {
+        unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad, u32 *__restrict__ seg_bad) {
     extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -898,6 +898,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
             const float gr = __fsub_rn(jac, jprev);
             const float err = __uint_as_float(~(u32)(e >> 32));
+            flag_nonfinite(~(u32)(e >> 32), seg_bad + seg);
             acc.add(err, gr);
             if (ug) ug[pay & kPayloadIdx] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
         }

@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["pack_partials", "ShardedMeanOfImages", "sharded_per_image_mean", "lovasz_softmax_sharded",
+           "hybrid_ce_lovasz_sharded", "losses_from_packed",
            "all_reduce_confusion", "shard_range"]
 
 
@@ -32,15 +33,28 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def pack_partials(group_loss: torch.Tensor, class_loss: torch.Tensor, class_present: torch.Tensor) -> torch.Tensor:
-    """fp64 buffer [sum_b loss_b, B_local, sum_b class_loss[b,:], sum_b present[b,:]]."""
+def pack_partials(group_loss: torch.Tensor, class_loss: torch.Tensor, class_present: torch.Tensor,
+                  ce_sum=None, n_valid=None) -> torch.Tensor:
+    """fp64 buffer [sum_b loss_b, B_local, sum_b class_loss[b,:], sum_b present[b,:], CE sum, valid pixels]
+    - the layout k_finalize writes (include/rtda_lovasz.h, `packed`); the last two are 0 without the
+    cross-entropy term."""
     c = class_loss.size(-1)
-    buf = torch.zeros(2 + 2 * c, dtype=torch.float64, device=group_loss.device)
+    buf = torch.zeros(4 + 2 * c, dtype=torch.float64, device=group_loss.device)
     buf[0] = group_loss.double().sum()
     buf[1] = float(group_loss.numel())
     buf[2:2 + c] = class_loss.double().view(-1, c).sum(0)
-    buf[2 + c:] = class_present.double().view(-1, c).sum(0)
+    buf[2 + c:2 + 2 * c] = class_present.double().view(-1, c).sum(0)
+    if ce_sum is not None:
+        buf[2 + 2 * c] = float(ce_sum)
+        buf[3 + 2 * c] = float(n_valid)
     return buf
+
+
+def losses_from_packed(packed: torch.Tensor, n_class: int):
+    """(Lovasz loss, cross-entropy, valid pixels) of the WHOLE batch from the all-reduced partial buffer:
+    mean over all images of the per-image losses; sum of -log p_label over all valid pixels / their number."""
+    k = 2 + 2 * n_class
+    return (packed[0] / packed[1]).float(), (packed[k] / packed[k + 1]).float(), packed[k + 1]
 
 
 class ShardedMeanOfImages(torch.autograd.Function):
@@ -70,12 +84,13 @@ def sharded_per_image_mean(group_loss, class_loss, class_present, group=None):
     packed = pack_partials(group_loss.detach(), class_loss.detach(), class_present.detach())
     loss, packed = ShardedMeanOfImages.apply(group_loss.sum(), packed, group)
     c = class_loss.size(-1)
-    counts = packed[2 + c:]
+    counts = packed[2 + c:2 + 2 * c]
     stats = dict(images=packed[1], class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
     return loss, stats
 
 
-def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None, global_images=None):
+def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None, global_images=None,
+                           grad_reduction="sum"):
     """per_image=True Lovasz-Softmax over a batch sharded across ranks: each rank passes its own
     images; every rank gets the global loss; gradients stay local.  The finalize kernel writes the
     partial buffer ``[sum of image losses, image count, class loss sums, class presence counts]``
@@ -85,11 +100,21 @@ def lovasz_softmax_sharded(probas_local, labels_local, ignore=255, group=None, g
     per-rank batch): the gradient then does not depend on the collective at all, so the all-reduce is
     issued asynchronously and the ranks no longer meet at a barrier inside every step.  The returned
     loss is this rank's share ``sum(local image losses) / global_images`` (the shares sum to the global
-    loss; gradients are identical); ``stats["loss"]`` is the global loss and waits for the collective."""
+    loss; gradients are identical) - NOT the loss itself; ``stats["loss"]`` is the global loss and waits
+    for the collective.
+
+    Gradient convention: the local gradient is scaled by ``1 / B_global``, which is right when the ranks'
+    parameter gradients are SUMMED.  ``DistributedDataParallel`` AVERAGES them; pass
+    ``grad_reduction="mean"`` there (the local gradient is then multiplied by the world size), otherwise
+    the parameter gradients come out ``world_size`` times smaller than on one device.
+
+    Memory: the sort workspace (0.55 GB for 4x19x512x1024, 3.9 GB for 16x19x720x1280) is cached per
+    (device, stream) until ``lovasz_loss.release_workspaces()``."""
     from .lovasz_loss import lovasz_softmax
 
     loss, outs = lovasz_softmax(probas_local, labels_local, per_image=True, ignore=ignore, return_outputs=True,
-                                shard_group=True if group is None else group, global_images=global_images)
+                                shard_group=True if group is None else group, global_images=global_images,
+                                grad_reduction=grad_reduction)
     return loss, _ShardStats(outs, probas_local.size(1))
 
 
@@ -102,11 +127,29 @@ class _ShardStats(dict):
 
     def __missing__(self, key):
         packed, c = self._outs.packed, self._c
-        counts = packed[2 + c:]
+        counts = packed[2 + c:2 + 2 * c]
         vals = dict(images=packed[1], loss=(packed[0] / packed[1]).float(),
-                    class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts)
+                    class_loss_mean=packed[2:2 + c] / counts.clamp(min=1), class_count=counts,
+                    valid_pixels=packed[3 + 2 * c], loss_ce=(packed[2 + 2 * c] / packed[3 + 2 * c].clamp(min=1)).float())
         self.update(vals)
         return vals[key]
+
+
+def hybrid_ce_lovasz_sharded(logits_local, labels_local, ignore=255, lovasz_weight=0.5, group=None,
+                             global_images=None, ce_reduction="global", grad_reduction="sum"):
+    """The training step's loss (train_lovasz.py:98-105) over a batch sharded across ranks, per-image
+    Lovasz semantics: ``CE + lovasz_weight * Lovasz`` from this rank's logits / labels; ONE all-reduce of
+    4+2C doubles; the backward is local.  With ``ce_reduction="global"`` (default) every rank gets
+    exactly the single-device numbers (cross-entropy over ALL ranks' valid pixels, Lovasz mean over all
+    images); ``"rank_mean"`` (needs ``global_images``) keeps the collective off the data path and
+    returns this rank's shares.  See hybrid_loss.hybrid_ce_lovasz.  Returns (total, ce, lovasz, stats)."""
+    from .hybrid_loss import hybrid_ce_lovasz
+
+    total, ce, lov, (outs, _probas) = hybrid_ce_lovasz(
+        logits_local, labels_local, ignore=ignore, lovasz_weight=lovasz_weight, per_image=True, return_outputs=True,
+        shard_group=True if group is None else group, global_images=global_images, ce_reduction=ce_reduction,
+        grad_reduction=grad_reduction)
+    return total, ce, lov, _ShardStats(outs, logits_local.size(1))
 
 
 def all_reduce_confusion(hist: torch.Tensor, group=None) -> torch.Tensor:

@@ -79,15 +79,15 @@ def mean(l, ignore_nan=False, empty=0):
 class LovaszOutputs:
     """Side outputs of a forward (device tensors, created lazily as views of one small buffer;
     reading them never synchronises): ``class_loss`` [G,C] fp32, ``class_present`` [G,C] i32,
-    ``n_present`` [G] i32, ``group_loss`` [G] fp32, ``label_errors`` [1] i32, ``packed`` [2+2C] f64
+    ``n_present`` [G] i32, ``group_loss`` [G] fp32, ``label_errors`` [1] i32, ``packed`` [4+2C] f64
     (see include/rtda_lovasz.h; after a sharded forward ``packed`` holds the all-reduced sums)."""
 
     def __init__(self, buf, groups, classes):
         self._buf, self._g, self._c = buf, groups, classes
         self._work = None    # pending asynchronous all-reduce of `packed` (sharded forward with global_images)
         g, c = groups, classes
-        o = 8 * (2 + 2 * c)
-        self._off = dict(packed=(0, 2 + 2 * c, torch.float64), loss=(o, 1, torch.float32),
+        o = 8 * (4 + 2 * c)
+        self._off = dict(packed=(0, 4 + 2 * c, torch.float64), loss=(o, 1, torch.float32),
                          label_errors=(o + 4, 1, torch.int32), loss_ce=(o + 8, 1, torch.float32),
                          n_valid=(o + 12, 1, torch.int32), n_present=(o + 16, g, torch.int32),
                          group_loss=(o + 16 + 4 * g, g, torch.float32),
@@ -96,7 +96,7 @@ class LovaszOutputs:
 
     @staticmethod
     def nbytes(groups, classes):
-        return 8 * (2 + 2 * classes) + 16 + 8 * groups + 8 * groups * classes
+        return 8 * (4 + 2 * classes) + 16 + 8 * groups + 8 * groups * classes
 
     def ptr(self, name):
         return self._buf.data_ptr() + self._off[name][0]
@@ -134,19 +134,27 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 # caching allocator and cost milliseconds of cudaMalloc on large batches.  Work on one stream is
 # ordered, so successive calls can share it.  release_workspaces() frees them.
 _workspaces = {}
+_graph_held = []   # workspaces handed out while a CUDA graph was being captured: the graph replays their address
 
 
-def release_workspaces() -> None:
+def release_workspaces(captured: bool = False) -> None:
+    """Drops the cached workspaces.  Those a captured CUDA graph points to are kept unless
+    ``captured=True`` (only after every such graph has been destroyed)."""
     _workspaces.clear()
+    if captured:
+        _graph_held.clear()
 
 
 def _workspace(dev, stream_ptr, nbytes):
     key = (dev.index, stream_ptr)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        _workspaces.pop(key, None)
+        # a larger shape arrived: the smaller buffer leaves the cache; it is freed here unless a captured
+        # graph holds it (below), in which case it lives on in _graph_held and the graph stays valid
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
+    if torch.cuda.is_current_stream_capturing() and not any(w is ws for w in _graph_held):
+        _graph_held.append(ws)
     return ws
 
 
@@ -211,7 +219,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
     packed partials and returns the global mean; the backward needs no collective."""
 
     @staticmethod
-    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None):
+    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None, grad_reduction="sum"):
         need_grad = bool(ctx.needs_input_grad[0])
         loss, (unit, codes), outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
         if holder is not None:
@@ -224,10 +232,12 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
 
             packed = outs.packed
             grp = None if shard_group is True else shard_group
+            # DistributedDataParallel averages the ranks' gradients: "mean" pre-multiplies by the world size
+            dscale = float(dist.get_world_size(grp)) if grad_reduction == "mean" else 1.0
             if global_images is None:
                 dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=grp)
                 loss = (packed[0] / packed[1]).float()
-                ctx.shard_scale = (float(probas.size(0)) / packed[1]).float()   # B_local / B_global, on the device
+                ctx.shard_scale = (float(probas.size(0)) * dscale / packed[1]).float()   # B_local / B_global, on the device
             else:
                 # the global image count is known: nothing on this rank's data path depends on the
                 # collective.  The forward returns this rank's SHARE of the global mean (the shares sum
@@ -239,7 +249,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
                     prev._packed()                      # at most one collective in flight per device (stream-side wait only)
                 outs._work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=grp, async_op=True)
                 _pending_reduce[probas.device.index] = outs
-                ctx.shard_scale = float(probas.size(0)) / float(global_images)
+                ctx.shard_scale = float(probas.size(0)) * dscale / float(global_images)
         if need_grad:
             ctx.save_for_backward(unit, codes, outs.class_present, outs.n_present)
         return loss
@@ -261,7 +271,7 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
             go.data_ptr(), unit.data_ptr(), codes.data_ptr(), present.data_ptr(), n_present.data_ptr(),
             b, c, h * w, int(ctx.per_image), grad.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
-        return grad, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None
 
 
 def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
@@ -274,6 +284,8 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
     if probas.dtype != torch.float32:
         probas = probas.float()  # the reference promotes through `fg.float() - probas_c` (:171)
     probas = probas.contiguous()  # NCHW; a channels_last tensor is re-laid out once
+    if probas.data_ptr() % 16 and (probas.size(2) * probas.size(3)) % 4 == 0:
+        probas = probas.clone()   # a contiguous view at an odd offset: the float4 paths need 16-byte alignment
     labels.view(-1)  # same failure as lovasz_loss.py:118 for a non-contiguous target
     if labels.dtype not in (torch.int64, torch.int32, torch.uint8):
         labels = labels.long()
@@ -283,7 +295,8 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
 
 
 def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
-                   validate_labels=False, return_outputs=False, shard_group=None, global_images=None):
+                   validate_labels=False, return_outputs=False, shard_group=None, global_images=None,
+                   grad_reduction="sum"):
     """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
     computes, lovasz_loss.py:185-200).
 
@@ -293,17 +306,23 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
     ``shard_group`` (a process group, or True for the default group) with ``per_image=True``
     treats ``probas`` as this rank's slice of a batch sharded over the ranks (see dist.py);
     with ``global_images`` (the batch size over all ranks) the collective is asynchronous and the
-    returned loss is this rank's share of the global mean.
+    returned loss is this rank's SHARE of the global mean (the shares sum to it), not the loss itself.
+    The local gradient is scaled by ``B_local / B_global`` so that the SUM of the ranks' parameter
+    gradients is the single-device gradient; ``grad_reduction="mean"`` multiplies it by the world size
+    for DistributedDataParallel, which averages gradients.
     """
     if classes not in ("present", "all"):
         raise ValueError("classes must be 'present' or 'all'")
+    if grad_reduction not in ("sum", "mean"):
+        raise ValueError("grad_reduction must be 'sum' or 'mean'")
     probas, labels = _as_kernel_inputs(probas, labels)
     if probas.numel() == 0:
         return probas.sum() * 0.0  # lovasz_loss.py:135-136
     if shard_group is not None and not per_image:
         raise ValueError("only per_image=True shards over ranks (global mode needs one sort over all pixels)")
     holder = []
-    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group, global_images)
+    loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group, global_images,
+                                        grad_reduction)
     outs = holder[0]
     if validate_labels:
         bad = int(outs.label_errors.item())
@@ -357,16 +376,25 @@ def lovasz_grad(gt_sorted):
 class LovaszSoftmax(nn.Module):
     """``LovaszSoftmax(ignore=255)(probas, labels)`` as in the reference
     (lovasz_loss.py:76-200; constructed at main.py:299-302 and
-    main_adversarial.py:233-237).  Stateless; ``per_image`` and
-    ``validate_labels`` are additions (see the module docstring)."""
+    main_adversarial.py:233-237).  Stateless; ``per_image``,
+    ``validate_labels`` and ``capture`` (CUDA-graph replay, graphed.py) are additions (see the module docstring)."""
 
-    def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False):
+    def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False, capture=False):
         super().__init__()
         self.reduction = reduction
         self.ignore = ignore
         self.per_image = per_image
         self.validate_labels = validate_labels
         self.last_outputs = None
+        # capture=True: one CUDA graph of the forward and one of the backward per input shape (graphed.py)
+        if capture and validate_labels:
+            raise ValueError("validate_labels reads a device counter on the host every step; it cannot be captured")
+        self._graphed = None
+        if capture:
+            from .graphed import GraphedCriterion
+
+            self._graphed = GraphedCriterion(lambda p, l: (lovasz_softmax(p, l, classes="present", per_image=self.per_image,
+                                                                          ignore=self.ignore),))
 
     def prob_flatten(self, input, target):
         """[B,C,H,W] -> [B*H*W, C] and [B,H,W] -> [B*H*W] (lovasz_loss.py:93-120)."""
@@ -377,8 +405,20 @@ class LovaszSoftmax(nn.Module):
         return lovasz_softmax_flat(probas, labels, classes=classes, ignore=self.ignore)
 
     def forward(self, probas, labels):
+        if self._graphed is not None and probas.numel() and not torch.cuda.is_current_stream_capturing():
+            probas, labels = _as_kernel_inputs(probas, labels)
+            (loss,) = self._graphed(probas, labels)
+            self.last_outputs = None          # the side outputs live in the graph's static buffers
+            return loss
         loss, outs = lovasz_softmax(probas, labels, classes="present", per_image=self.per_image,
                                     ignore=self.ignore, validate_labels=self.validate_labels,
                                     return_outputs=True) if probas.numel() else (lovasz_softmax(probas, labels), None)
         self.last_outputs = outs
         return loss
+
+    def static_inputs(self, probas_like, labels_like):
+        """capture=True: the static (probas, labels) buffers of this shape; a producer that writes into
+        them (e.g. ``torch.softmax(logits, 1, out=buf)``) saves the per-step input copy."""
+        if self._graphed is None:
+            raise RuntimeError("static_inputs needs capture=True")
+        return self._graphed.static_inputs(*_as_kernel_inputs(probas_like, labels_like))

@@ -53,10 +53,16 @@ def confusion_matrix(labels, preds, n_class=19, ignore_index=255, out=None):
     (validation.py:102-107 + utils.py:78-87).  Returns a CUDA int64 [n,n] tensor;
     pass ``out`` to accumulate into an existing one."""
     lib = _lib.load()
+    if out is not None:
+        # the kernel does 64-bit atomics on n_class^2 slots of `out`: anything else is an out-of-bounds write
+        if (not torch.is_tensor(out) or out.dtype != torch.int64 or not out.is_cuda or not out.is_contiguous()
+                or out.numel() != n_class * n_class):
+            raise ValueError("out must be a contiguous CUDA int64 tensor with n_class*n_class elements")
     if (out is not None and torch.is_tensor(labels) and torch.is_tensor(preds) and labels.is_cuda and preds.is_cuda
             and labels.dtype in _INT_KINDS and preds.dtype in _INT_KINDS and labels.is_contiguous()
-            and preds.is_contiguous() and labels.numel() == preds.numel()):
-        # fast path of a validation loop: device maps, existing accumulator - one C call, no checks repeated
+            and preds.is_contiguous() and labels.numel() == preds.numel()
+            and labels.device == out.device and preds.device == out.device):
+        # fast path of a validation loop: device maps, existing accumulator - one C call
         dev = labels.device
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
@@ -70,10 +76,12 @@ def confusion_matrix(labels, preds, n_class=19, ignore_index=255, out=None):
     preds = _as_device_ints(preds, dev)
     if labels.numel() != preds.numel():
         raise ValueError(f"labels {tuple(labels.shape)} and preds {tuple(preds.shape)} differ in size")
+    if torch.is_tensor(preds) and preds.is_cuda and preds.device != dev:
+        raise ValueError(f"labels are on {dev} and preds on {preds.device}")
     if out is None:
         out = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
-    elif out.dtype != torch.int64 or not out.is_cuda or out.numel() != n_class * n_class or not out.is_contiguous():
-        raise ValueError("out must be a contiguous CUDA int64 tensor with n_class*n_class elements")
+    elif out.device != dev:
+        raise ValueError(f"out is on {out.device} and the maps on {dev}")
     with torch.cuda.device(dev):
         _lib.check(lib.rtda_confusion_accumulate(
             labels.data_ptr(), _lib.label_kind(labels.dtype), preds.data_ptr(), _lib.label_kind(preds.dtype),
@@ -98,6 +106,9 @@ def confusion_matrix_from_logits(logits, labels, ignore_index=255, out=None):
         raise ValueError("labels do not match logits")
     if out is None:
         out = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    elif (not torch.is_tensor(out) or out.dtype != torch.int64 or not out.is_cuda or not out.is_contiguous()
+          or out.numel() != n_class * n_class or out.device != dev):
+        raise ValueError("out must be a contiguous CUDA int64 tensor with n_class*n_class elements on the logits' device")
     with torch.cuda.device(dev):
         _lib.check(lib.rtda_confusion_argmax_accumulate(
             logits.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype), b, n_class, h * w,

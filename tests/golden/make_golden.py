@@ -100,6 +100,26 @@ def tie_cases():
     return cases
 
 
+def midsize_cases():
+    """Mid-size cases regenerated from the synthetic generators at test time (the inputs are not stored:
+    10 MB each); the fixture holds what the reference returned for them: the loss, the sum of |gradient|
+    per class, 4096 sampled gradient entries, and a checksum of the inputs so that a drift of the
+    generator is noticed.  name -> (b, h, w, seed, scale, boost, per_image)."""
+    return {
+        "mid_conf_1x19x256x512": (1, 256, 512, 7001, 3.0, 6.0, False),           # D_conf: > 1 bucket per segment, k_plan's linear maps
+        "mid_saturated_1x19x192x384": (1, 192, 384, 7002, 3.0, 16.0, False),     # boost 16: exact ties at 1 - k * 2^-24
+        "mid_conf_per_image_2x19x160x256": (2, 160, 256, 7003, 3.0, 6.0, True),
+    }
+
+
+def midsize_inputs(b, h, w, seed, scale, boost):
+    from rtda_semanticsegmentation_b200 import synthetic
+
+    labels = synthetic.blocky_labels(b, h, w, seed=seed)
+    logits = synthetic.confident_logits(labels, seed=seed, scale=scale, boost=boost)
+    return torch.softmax(logits, 1), labels
+
+
 def hist_cases():
     cases = {}
     g = np.random.default_rng(31)
@@ -157,6 +177,26 @@ def main():
     out["lovasz_grad/count"] = np.asarray(5, np.int64)
     np.savez_compressed(os.path.join(HERE, "lovasz_golden.npz"), names=np.asarray(meta), **out)
 
+    mout = {}
+    mnames = []
+    for name, (b, h, w, seed, scale, boost, per_image) in midsize_cases().items():
+        p, l = midsize_inputs(b, h, w, seed, scale, boost)
+        _, loss32, grad, _ = run_ref(p, l, 255, per_image)
+        rng = np.random.default_rng(seed)
+        nz = np.flatnonzero(grad.ravel())
+        idx = np.sort(np.concatenate([rng.choice(nz, 3072, replace=False), rng.integers(0, grad.size, 1024)]))
+        mout[f"{name}/spec"] = np.asarray([b, h, w, seed, per_image], np.int64)
+        mout[f"{name}/scale_boost"] = np.asarray([scale, boost], np.float64)
+        mout[f"{name}/input_checksum"] = np.asarray([int(p.view(torch.int32).to(torch.int64).sum()), int(l.sum())], np.int64)
+        mout[f"{name}/loss"] = np.asarray(loss32, np.float32)
+        mout[f"{name}/abs_grad_per_class"] = np.abs(grad.astype(np.float64)).sum(axis=(0, 2, 3))
+        mout[f"{name}/grad_idx"] = idx.astype(np.int64)
+        mout[f"{name}/grad_val"] = grad.ravel()[idx].astype(np.float32)
+        mout[f"{name}/grad_max"] = np.asarray(np.abs(grad).max(), np.float32)
+        mout[f"{name}/exact_one_probabilities"] = np.asarray(int((p == 1.0).sum()), np.int64)
+        mnames.append(name)
+    np.savez_compressed(os.path.join(HERE, "lovasz_midsize_golden.npz"), names=np.asarray(mnames), **mout)
+
     hout = {}
     hnames = []
     for name, (t, p, n) in hist_cases().items():
@@ -182,7 +222,7 @@ def main():
     hout["val_slice/iou"] = np.asarray(utl.per_class_iou(h.astype(np.float64)), np.float64)
     hout["val_slice/miou"] = np.asarray(float(np.nanmean(utl.per_class_iou(h.astype(np.float64)))), np.float64)
     np.savez_compressed(os.path.join(HERE, "hist_golden.npz"), names=np.asarray(hnames), **hout)
-    print("wrote", len(meta), "lovasz cases and", len(hnames) + 1, "hist cases")
+    print("wrote", len(meta), "lovasz cases,", len(mnames), "mid-size cases and", len(hnames) + 1, "hist cases")
 
 
 if __name__ == "__main__":

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_error_strings(lib):
-    assert lib.rtda_version() == 1
+    assert lib.rtda_version() == 2
     assert lib.rtda_error_string(0) == b"ok"
     for code in (-1, -2, -3, -4):
         assert lib.rtda_error_string(code).startswith(b"rtda:")

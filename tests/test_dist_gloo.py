@@ -13,7 +13,8 @@ import torch.multiprocessing as mp
 
 from oracle import c_oracle, hist_oracle
 from rtda_semanticsegmentation_b200 import synthetic
-from rtda_semanticsegmentation_b200.dist import all_reduce_confusion, shard_range, sharded_per_image_mean
+from rtda_semanticsegmentation_b200.dist import (all_reduce_confusion, losses_from_packed, pack_partials, shard_range,
+                                                 sharded_per_image_mean)
 
 
 def _free_port():
@@ -38,12 +39,22 @@ def _worker(rank, world, port, out_dir):
         group_loss.requires_grad_(True)
         loss, stats = sharded_per_image_mean(group_loss, cl, pres)
         loss.backward()
+        # fused CE + Lovasz sharded (configs[2], [4]): the buffer k_finalize packs, with this rank's CE sum and
+        # valid-pixel count, all-reduced once; the global losses come from the reduced buffer
+        logits = synthetic.confident_logits(labels, seed=77)
+        lg, lb = logits[lo:hi], labels[lo:hi]
+        nv = int((lb != 255).sum())
+        ce_sum = float(torch.nn.functional.cross_entropy(lg, lb, ignore_index=255, reduction="sum").double()) if nv else 0.0
+        packed = pack_partials(group_loss.detach(), cl, pres, ce_sum=ce_sum, n_valid=nv)
+        dist.all_reduce(packed)
+        h_lov, h_ce, h_nv = losses_from_packed(packed, 19)
         lab, prd = synthetic.validation_maps(6, 32, 32, seed=78)
         lo2, hi2 = shard_range(6, rank, world)
         h = torch.from_numpy(hist_oracle.validation_confusion(lab[lo2:hi2].numpy(), prd[lo2:hi2].numpy(), 19, 255))
         all_reduce_confusion(h)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss.detach().numpy(), grad=group_loss.grad.numpy(),
-                 hist=h.numpy(), images=stats["images"].numpy(), counts=stats["class_count"].numpy())
+                 hist=h.numpy(), images=stats["images"].numpy(), counts=stats["class_count"].numpy(),
+                 h_lov=h_lov.numpy(), h_ce=h_ce.numpy(), h_nv=h_nv.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -57,8 +68,13 @@ def test_world_size_2_sharding(tmp_path):
     want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, per_image=True)
     lab, prd = synthetic.validation_maps(6, 32, 32, seed=78)
     want_hist = hist_oracle.validation_confusion(lab.numpy(), prd.numpy(), 19, 255)
+    logits = synthetic.confident_logits(labels, seed=77)
+    want_ce = float(torch.nn.functional.cross_entropy(logits, labels, ignore_index=255))   # train_lovasz.py:98 on the whole batch
     for rank in range(world):
         z = np.load(tmp_path / f"r{rank}.npz")
+        assert float(z["h_ce"]) == pytest.approx(want_ce, rel=1e-6)                  # CE over ALL ranks' valid pixels
+        assert float(z["h_lov"]) == pytest.approx(float(want["loss"]), rel=1e-6)
+        assert float(z["h_nv"]) == float((labels != 255).sum())
         assert float(z["loss"]) == pytest.approx(float(want["loss"]), rel=1e-6)      # every rank holds the global loss
         assert np.allclose(z["grad"], 1.0 / 4.0)                                     # d loss / d loss_b = 1 / B_global
         assert np.array_equal(z["hist"], want_hist)                                  # bit-exact counts

@@ -70,6 +70,19 @@ def test_golden_vectors(lovasz_golden):
             assert np.array_equal(grad, c["grad"]), name        # in fact bit for bit
 
 
+def test_midsize_reference_fixture(midsize_golden):
+    """Reference-generated mid-size cases: more than one bucket per segment, k_plan's linear
+    maps, the tie spreading of saturated predictions - against numbers recorded from the unmodified reference."""
+    from conftest import assert_midsize, midsize_case
+
+    for name in [str(n) for n in midsize_golden["names"]]:
+        c = midsize_case(midsize_golden, name)
+        loss, grad = run_cuda(c["probas"], c["labels"], 255, c["per_image"])
+        assert_midsize(c, loss, grad, name)
+        want = c_oracle.lovasz(c["probas"].numpy(), c["labels"].numpy(), 255, c["per_image"])
+        assert np.array_equal(grad, want["grad"]), name        # and bit for bit against the stable oracle
+
+
 def test_kat1_by_hand():
     # SURVEY.md section 4 KAT1: loss 0.5666666627, grads known in closed form
     ch1 = torch.tensor([0.9, 0.6, 0.3, 0.2])

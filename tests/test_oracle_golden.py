@@ -92,3 +92,15 @@ def test_hist_oracle_matches_fixtures(hist_golden):
     assert np.array_equal(hist_oracle.validation_confusion(lab, prd, 19, 255), z["val_slice/hist"])
     assert np.array_equal(c_oracle.confusion(lab, prd, 19, 255), z["val_slice/hist"])
     assert hist_oracle.mean_iou(z["val_slice/hist"].astype(np.float64)) == float(z["val_slice/miou"])
+
+
+def test_c_oracle_against_midsize_reference_fixture(midsize_golden):
+    """Mid-size cases (several buckets per segment on the GPU, saturated predictions with exact ties) recorded
+    from the unmodified reference: loss, per-class sum of |gradient|, 4096 sampled gradient entries."""
+    from conftest import assert_midsize, midsize_case
+    from oracle import c_oracle
+
+    for name in [str(n) for n in midsize_golden["names"]]:
+        c = midsize_case(midsize_golden, name)
+        r = c_oracle.lovasz(c["probas"].numpy(), c["labels"].numpy(), 255, c["per_image"])
+        assert_midsize(c, float(r["loss"]), r["grad"], name)
