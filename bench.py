@@ -631,6 +631,7 @@ def main():
     # ---- timed region 1a: the same public call launched eagerly (no graph, no profiling events): what a
     # caller of criterion(probas, labels); loss.backward() gets without capturing anything
     eager = Stepper(crit, sets, dev, world, use_graph=False)
+    eager.run(3)                                   # untimed: the allocator's blocks of the eager path exist again after the captures
     ms_eager, _ = timed(lambda: eager.run(args.steps), barrier, dev, world)
     eager_ms_step = ms_eager / args.steps
 
