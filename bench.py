@@ -323,7 +323,26 @@ def measure_confusion(rank, dev, world, steps, warmup, batch=1, use_graph=True, 
     per = k_ms / max(k_n, 1)
     peak, peak_src = peaks()
     achieved = CM_BYTES_PER_PX * px / (per * 1e-3) / 1e9 if per > 0 else 0.0
-    return dict(value=world * px / (ms_step * 1e-3) / 1e6, ms_per_step=ms_step, steps=steps, maps_per_step=batch, px=px,
+    # calibration: what a plain device copy moving the SAME number of bytes reaches at this size (the measured
+    # peak is a 2 GB transfer; a 33 MB one pays launch, ramp-up and tail like any kernel of a few microseconds)
+    src = [torch.empty(px, dtype=torch.int64, device=dev) for _ in range(n_sets)]
+    dst = torch.empty(px, dtype=torch.int64, device=dev)
+    for a in src:
+        dst.copy_(a)
+    cal_ms_graph = None
+    try:
+        gcal = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gcal):
+            for a in src:
+                dst.copy_(a)
+        ms_cal, _ = timed(lambda: [gcal.replay() for _ in range(4)], barrier, dev, world)
+        cal_ms_graph = ms_cal / (4 * n_sets)
+    except Exception:  # noqa: BLE001
+        pass
+    del src, dst
+    return dict(copy_same_bytes_ms=cal_ms_graph,
+                copy_same_bytes_frac=(CM_BYTES_PER_PX * px / (cal_ms_graph * 1e-3) / 1e9 / peak) if cal_ms_graph else None,
+                value=world * px / (ms_step * 1e-3) / 1e6, ms_per_step=ms_step, steps=steps, maps_per_step=batch, px=px,
                 launch="cuda_graph replay" if graph is not None else "eager", counted_pixels=total, n_sets=n_sets,
                 kernel_ms=per, kernel_launches=int(k_n), achieved=achieved, frac=achieved / peak, peak=peak,
                 peak_src=peak_src, maps=maps)
@@ -356,12 +375,12 @@ def bench_confusion(args, rank, local_rank, world):
     # end to end through the reference signature: numpy maps on the host -> fast_hist -> numpy matrix
     host = [(l[0].cpu().numpy().ravel(), p[0].cpu().numpy().ravel()) for l, p in maps[:3]]
     for i in range(3):
-        rtda.fast_hist(*host[i % 3], 19)
+        rtda.fast_hist(*host[i % len(host)], 19)
     barrier()
     t0 = time.perf_counter()
     acc = np.zeros((19, 19))
     for i in range(args.steps):
-        acc += rtda.fast_hist(*host[i % 3], 19)
+        acc += rtda.fast_hist(*host[i % len(host)], 19)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     if rank != 0:
         if world > 1:
@@ -383,7 +402,10 @@ def bench_confusion(args, rank, local_rank, world):
         "gpu_launches": m["kernel_launches"],
         "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": m["peak"], "unit": "GB/s", "frac": m["frac"],
                      "traffic": None, "peak_source": m["peak_src"], "dominant_kernel": "k_confusion",
-                     "ms_per_launch": m["kernel_ms"], "what": "16 B/px (int64 label + int64 prediction) x pixels per call / k_confusion CUDA-event time"},
+                     "ms_per_launch": m["kernel_ms"], "what": "16 B/px (int64 label + int64 prediction) x pixels per call / k_confusion CUDA-event time (two events around every eager launch)",
+                     "frac_graph_replay": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"],
+                     "plain_copy_of_the_same_bytes": {"ms": m["copy_same_bytes_ms"], "frac_of_peak": m["copy_same_bytes_frac"],
+                                                      "what": "torch copy_ of the same number of bytes (read + write), graph-replayed back to back: the ceiling a kernel of this size can reach"}},
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle import hist_oracle
@@ -724,7 +746,9 @@ def main():
                 secondary[f"c4_confusion_{batch}map"] = {
                     "workload": "c4: " + WORKLOADS["c4"][4], "maps_per_call": batch, "value": m["value"], "unit": "Mpix/s",
                     "ms_per_step": m["ms_per_step"], "launch": m["launch"], "kernel_ms_per_launch": m["kernel_ms"],
-                    "roofline_frac": m["frac"], "achieved_gbs_per_gpu": m["achieved"], "scaling": "weak"}
+                    "roofline_frac": m["frac"], "achieved_gbs_per_gpu": m["achieved"], "scaling": "weak",
+                    "roofline_frac_graph_replay": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"] / world * world,
+                    "plain_copy_of_the_same_bytes": {"ms": m["copy_same_bytes_ms"], "frac_of_peak": m["copy_same_bytes_frac"]}}
                 torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001
                 secondary[f"c4_confusion_{batch}map"] = {"error": repr(e)[:300]}

@@ -84,6 +84,106 @@ k_confusion(const LabelT *__restrict__ labels, const PredT *__restrict__ preds, 
     cm_flush<MODE>(sh, nbins, hist);
 }
 
+// ---------------------------------------------------------------------------
+// k_confusion_stream: the streaming form for maps whose bins fit a shared histogram and whose pointers
+// allow vector loads - the validation loop's case.
+//
+//   * a thread owns kCmsRun * V CONSECUTIVE pixels (8 for int64 maps: four 16-byte loads per map), all
+//     loads issued before any pixel is looked at: 1024 resident threads keep 128 KB per SM in flight;
+//   * label maps are spatially coherent and predictions mostly right, so the pixels of a thread mostly share
+//     one bin: the thread counts that bin in a register and only the others go to the shared histogram one
+//     by one; one more atomic per thread delivers the register count.  About 0.3 shared atomics per pixel
+//     on the 80 %-right synthetic maps, fewer on real ones, and no warp-wide operation at all;
+//   * the lanes of a warp are kCmsRun * V pixels apart, i.e. in different label tiles: the atomics of one
+//     warp instruction mostly hit different bins (few same-address replays);
+//   * ONE histogram per block (n_class^2 words): zeroing and the flush touch 361 words, not 32 x 361;
+//     blocks take equal contiguous chunks, two 512-thread blocks per SM.
+#ifndef RTDA_CM_THREADS
+#define RTDA_CM_THREADS 512
+#endif
+#ifndef RTDA_CM_BLOCKS_PER_SM
+#define RTDA_CM_BLOCKS_PER_SM 2
+#endif
+#ifndef RTDA_CM_RUN
+#define RTDA_CM_RUN 4
+#endif
+constexpr int kCmsThreads = RTDA_CM_THREADS;
+constexpr int kCmsRun = RTDA_CM_RUN;
+
+template <typename T, int V> struct VecLoad;      // V consecutive elements of type T in one load
+template <typename T> struct VecLoad<T, 1> { static __device__ __forceinline__ void ld(const T *p, long long *o) { o[0] = (long long)*p; } };
+template <> struct VecLoad<long long, 2> {
+    static __device__ __forceinline__ void ld(const long long *p, long long *o) {
+        const longlong2 v = *reinterpret_cast<const longlong2 *>(p); o[0] = v.x; o[1] = v.y; }
+};
+template <> struct VecLoad<int, 2> {
+    static __device__ __forceinline__ void ld(const int *p, long long *o) {
+        const int2 v = *reinterpret_cast<const int2 *>(p); o[0] = v.x; o[1] = v.y; }
+};
+template <> struct VecLoad<unsigned char, 2> {
+    static __device__ __forceinline__ void ld(const unsigned char *p, long long *o) {
+        const uchar2 v = *reinterpret_cast<const uchar2 *>(p); o[0] = v.x; o[1] = v.y; }
+};
+template <> struct VecLoad<int, 4> {
+    static __device__ __forceinline__ void ld(const int *p, long long *o) {
+        const int4 v = *reinterpret_cast<const int4 *>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct VecLoad<unsigned char, 4> {
+    static __device__ __forceinline__ void ld(const unsigned char *p, long long *o) {
+        const uchar4 v = *reinterpret_cast<const uchar4 *>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+
+template <typename LabelT, typename PredT, int V>
+__global__ void __launch_bounds__(kCmsThreads, RTDA_CM_BLOCKS_PER_SM)
+k_confusion_stream(const LabelT *__restrict__ labels, const PredT *__restrict__ preds, long long n, int n_class,
+                   long long ignore, int has_ignore, unsigned long long *__restrict__ hist) {
+    extern __shared__ u32 sh[];
+    constexpr int kPx = kCmsRun * V;                       // consecutive pixels of one thread item
+    const int nbins = n_class * n_class;
+    const u32 tid = threadIdx.x;
+    for (int i = tid; i < nbins; i += kCmsThreads) sh[i] = 0;
+    // this block's contiguous chunk of thread items; the last item of the map may be partial
+    const long long items = (n + kPx - 1) / kPx;
+    const long long per_block = (items + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per_block;
+    const long long hi = lo + per_block < items ? lo + per_block : items;
+    __syncthreads();
+    for (long long it = lo + tid; it < hi; it += kCmsThreads) {
+        long long t[kPx], p[kPx];
+        const long long px0 = it * kPx;
+        if (px0 + kPx <= n) {
+#pragma unroll
+            for (int r = 0; r < kCmsRun; ++r) {
+                VecLoad<LabelT, V>::ld(labels + px0 + r * V, t + r * V);
+                VecLoad<PredT, V>::ld(preds + px0 + r * V, p + r * V);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kPx; ++q) {
+                t[q] = -1; p[q] = -1;
+                if (px0 + q < n) { t[q] = (long long)labels[px0 + q]; p[q] = (long long)preds[px0 + q]; }
+            }
+        }
+        u32 cur = 0xffffffffu, cnt = 0;
+#pragma unroll
+        for (int q = 0; q < kPx; ++q) {
+            const bool ok = !(has_ignore && t[q] == ignore) &&                       // validation.py:102
+                            t[q] >= 0 && t[q] < n_class && p[q] >= 0 && p[q] < n_class;   // utils.py:78-83
+            if (!ok) continue;
+            const u32 bin = (u32)t[q] * (u32)n_class + (u32)p[q];                     // utils.py:84-87
+            if (bin == cur) ++cnt;
+            else if (cnt == 0) { cur = bin; cnt = 1; }
+            else atomicAdd(&sh[bin], 1u);
+        }
+        if (cnt) atomicAdd(&sh[cur], cnt);
+    }
+    __syncthreads();
+    for (int b = tid; b < nbins; b += kCmsThreads) {
+        const u32 s = sh[b];
+        if (s) atomicAdd(&hist[b], (unsigned long long)s);
+    }
+}
+
 // Fused validation.py:95 (argmax over classes, first maximum wins) + the histogram.
 template <typename LabelT, int MODE>
 __global__ void __launch_bounds__(kCmThreads)
@@ -144,6 +244,22 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
     const LabelT *l = (const LabelT *)labels;
     const PredT *p = (const PredT *)preds;
     ProfileScope ps(kStageConfusion, st);
+    {
+        // streaming form: V pixels per load (16 bytes of the wider map), when both pointers are aligned for it
+        constexpr int kWide = sizeof(LabelT) > sizeof(PredT) ? (int)sizeof(LabelT) : (int)sizeof(PredT);
+        constexpr int V = kWide == 8 ? 2 : 4;
+        const size_t ssm = (size_t)n_class * n_class * sizeof(u32);
+        if (ssm <= 40 * 1024 && ((uintptr_t)labels % (V * sizeof(LabelT))) == 0 && ((uintptr_t)preds % (V * sizeof(PredT))) == 0) {
+            const long long items = (n + kCmsRun * V - 1) / (kCmsRun * V);
+            long long sgrid = (long long)RTDA_CM_BLOCKS_PER_SM * sm_count();
+            const long long need = (items + kCmsThreads - 1) / kCmsThreads;          // at least one item per thread
+            if (sgrid > need) sgrid = need;
+            if (sgrid < 1) sgrid = 1;
+            k_confusion_stream<LabelT, PredT, V><<<(unsigned)sgrid, kCmsThreads, ssm, st>>>(l, p, n, n_class, ignore, has_ignore, h);
+            RTDA_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     if (mode == 0) {
         if (smem > 48 * 1024)
             RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion<LabelT, PredT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -512,8 +512,10 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 // (one shared-memory atomic per element returns the arrival ticket); W = 4 first, and if a field
 // overflows (16 or more elements in one slot: exact ties) the block starts over with W = 8 (16384
 // slots); with 256 or more in one slot the block sorts its whole bucket with a bitonic network instead.
-constexpr int kCntWords = 4096;          // 16 KB of packed counters: 32768 4-bit or 16384 8-bit fine slots
-constexpr int kColMax = 1024;            // dense list of the elements that share a fine slot
+constexpr int kCntWords = kBTile / 2;    // packed counters, 4 fine slots per slot of capacity: 16 KB = 32768 4-bit or 16384 8-bit fine slots for 8192
+constexpr int kColMax = kBTile / 8;      // dense list of the elements that share a fine slot
+constexpr int kSlotBits4 = kCntWords == 4096 ? 15 : 14;    // log2(kCntWords * 8)
+static_assert(kCntWords == 4096 || kCntWords == 2048, "fine-slot bits follow the counter words; the counter scan takes 128 words per warp and round");
 struct LocalShared {
     u64 stage[kBTile];                   // the bucket, in the order k_part wrote it
     u32 cntw[kCntWords];
@@ -544,7 +546,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
     const bool lin = lin_R != 0xFFFFFFFFu;           // block-uniform
     constexpr u32 FW = 32 / W;                       // fields per word
     constexpr u32 FM = (1u << W) - 1u;               // largest field value
-    constexpr u32 FSHIFT = (W == 4) ? 1 : 2;         // 16 fractional bits -> 15 / 14 bits of fine slot
+    constexpr u32 FSHIFT = (W == 4) ? (16 - kSlotBits4) : (17 - kSlotBits4);   // 16 fractional bits -> 15 / 14 bits of fine slot (at 4096 words)
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // phase A: one atomic per element; {fine slot:0..14, foreground:15, ticket:16..23}
@@ -816,7 +818,7 @@ k_plan(Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb, con
     out[2 * b + 1] = l;
 }
 
-__global__ void __launch_bounds__(kBThreads, 2)
+__global__ void __launch_bounds__(kBThreads, RTDA_LOCAL_BLOCKS)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u32 *__restrict__ ties, const uint4 *__restrict__ plan,
         unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad, u32 *__restrict__ seg_bad) {
