@@ -86,14 +86,22 @@ int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t
  * variable RTDA_SORT_PATH=lsd selects 1 at the first call. */
 int rtda_lovasz_set_sort_path(int path);
 
-/* Forward.  Outputs:
- *   unit_grad     [G][C][n] fp32, n = B*HW/G: d(sum of present class losses of the
- *                 group)/d(probas) for grad_out = 1 before the 1/K and 1/G factors,
- *                 i.e. -g_rank * sgn(fg - p); rows of absent classes and ignored pixels
- *                 are NOT written.  May be NULL (loss only, e.g. under torch.no_grad()).
+/* Where the forward leaves the gradient (`grad_mode`):
+ *   RTDA_GRAD_FINAL  `grad` [B][C][HW] fp32 (the caller's NCHW layout) receives d(loss)/d(probas) for
+ *                    grad_out = 1, complete: the 1/K and 1/G factors of the two means applied with the same
+ *                    fp32 divisions autograd performs, zeros at ignored pixels and in absent classes.  The
+ *                    sort kernels write it directly; there is no second pass over it.  The backward is
+ *                    rtda_lovasz_bwd_inplace: nothing to do for grad_out = 1, one in-place multiplication
+ *                    otherwise.  `applied_scale` [1] fp32 records which grad_out the buffer currently holds.
+ *   RTDA_GRAD_UNIT   `grad` [G][C][n] fp32, n = B*HW/G, receives the unit gradient -g_rank * sgn(fg - p)
+ *                    before the 1/K and 1/G factors; rows of absent classes and ignored pixels are NOT
+ *                    written.  The backward is rtda_lovasz_bwd (bit-exact for ANY grad_out) or, fused with the
+ *                    softmax and cross-entropy backward, rtda_hybrid_bwd; both read `codes` as well.
+ * Forward outputs:
+ *   grad          see above; may be NULL (loss only, e.g. under torch.no_grad()).
  *   codes         [B*HW] u8, 4-byte aligned when HW % 4 == 0: the class of every pixel, 255 = ignored or
- *                 out of range; required with unit_grad (the backward reads both), else
- *                 may be NULL.
+ *                 out of range; required with RTDA_GRAD_UNIT (its backward reads it), else may be NULL.
+ *   applied_scale [1] fp32, set to 1; required with RTDA_GRAD_FINAL, else may be NULL.
  *   loss          [1]    fp32  the scalar loss (0 when nothing is valid)
  *   class_loss    [G][C] fp32  per-class Lovasz losses (0 where absent)
  *   class_present [G][C] i32   1 where the class has a valid foreground pixel
@@ -110,14 +118,30 @@ int rtda_lovasz_set_sort_path(int path);
  * that class's loss NaN (or +inf) and the means carry it into `loss`, as torch.dot does in the
  * reference (lovasz_loss.py:180).  The gradient at such elements is unspecified (finite).
  */
+#define RTDA_GRAD_UNIT 0
+#define RTDA_GRAD_FINAL 1
+/* 1 when RTDA_GRAD_FINAL is available for this shape: always with one image per group (per_image, or B = 1);
+ * with several images per group it needs HW % 4096 == 0 and B*C*HW < 2^30 (rtda_lovasz_fwd returns
+ * RTDA_E_RANGE otherwise; use RTDA_GRAD_UNIT + rtda_lovasz_bwd there). */
+int rtda_lovasz_final_grad_supported(int64_t B, int C, int64_t HW, int per_image);
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
-                    void *ws, size_t ws_bytes,
-                    float *unit_grad, uint8_t *codes, float *loss, float *class_loss,
+                    void *ws, size_t ws_bytes, int grad_mode,
+                    float *grad, uint8_t *codes, float *applied_scale, float *loss, float *class_loss,
                     int32_t *class_present, int32_t *n_present, float *group_loss,
                     int32_t *label_errors, double *packed, void *stream);
 
-/* Backward: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) at valid pixels of
+/* Backward of RTDA_GRAD_FINAL, in place: grad_probas (the forward's `grad`) becomes
+ * d(loss * grad_out)/d(probas).  It holds the gradient for grad_out = *applied_scale; when grad_out equals
+ * that (the plain loss.backward()) the kernel exits at once, otherwise every element is multiplied by
+ * grad_out / *applied_scale and *applied_scale is updated - exact (bit-identical to the reference's fp32
+ * sequence (grad_out / G) / K * g) whenever that ratio is a power of two (a loss weight of 0.5, an AMP
+ * loss scale), within 3 ulp of it otherwise; rtda_lovasz_bwd is bit-exact for any grad_out.  grad_out is a
+ * DEVICE scalar; `ws` is the forward's workspace (one zeroed counter in its header is used). */
+int rtda_lovasz_bwd_inplace(const float *grad_out, float *grad_probas, float *applied_scale, void *ws,
+                            int64_t B, int C, int64_t HW, void *stream);
+
+/* Backward of RTDA_GRAD_UNIT: grad_probas[b][c][hw] = unit_grad * ((grad_out / G) / K_g) at valid pixels of
  * present classes, 0 elsewhere (the autograd of lovasz_loss.py:19-44,180); every element
  * of grad_probas [B][C][HW] is written.  grad_out is a DEVICE scalar; unit_grad, codes,
  * class_present and n_present are the forward's outputs. */

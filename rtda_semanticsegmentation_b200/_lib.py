@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("RTDA_LIB_PATH") or os.path.join(_PKG, "librtda_lovasz
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "rtda_lovasz.h")
 
 LABEL_I64, LABEL_U8, LABEL_I32 = 0, 1, 2
+GRAD_UNIT, GRAD_FINAL = 0, 1
 ABI_VERSION = 2   # RTDA_ABI_VERSION of include/rtda_lovasz.h
 
 # name -> (restype, argtypes); must list every function include/rtda_lovasz.h declares
@@ -28,8 +29,10 @@ SIGNATURES = {
     "rtda_lovasz_workspace_bytes": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "rtda_lovasz_debug_layout": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "rtda_lovasz_set_sort_path": (_int, [_int]),
-    "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz,
-                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz, _int,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtda_lovasz_final_grad_supported": (_int, [_i64, _int, _i64, _int]),
+    "rtda_lovasz_bwd_inplace": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _vp]),
     "rtda_lovasz_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _int, _vp, _vp]),
     "rtda_hybrid_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2)
 k_split(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
         const u32 *__restrict__ seg_fg, int force_lsd, u32 *__restrict__ ghist /*[S][kSplitWords], zeroed*/,
         u32 *__restrict__ table, u32 *__restrict__ ties, u32 *__restrict__ nb_out, u32 *__restrict__ fb_flag,
-        u32 *__restrict__ fb_any) {
+        u32 *__restrict__ fb_any, float *__restrict__ seg_scale, float *__restrict__ grad) {
     // hist: sample count per bin.  zc: how many of them sit exactly on the bin's first key (low 19
     // bits of tau = 0): the boundary ties cdf_pos spreads by pixel index.
     extern __shared__ u32 split_smem[];
@@ -138,7 +138,25 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     const u32 g = seg / (u32)geo.C, c = seg - g * (u32)geo.C;
     if (seg_fg[seg] == 0) {                       // class absent from this group
         if (tid == 0 && blockIdx.y == 0) nb_out[seg] = 0;
+        if (geo.final_grad && grad) {
+            // the final gradient has no separate zero-filling pass: the planes of an absent class are zeroed here
+            // (ignored pixels: k_prep; everything else is written by the kernels that sort the segment)
+            float *gb = grad_base(geo, grad, seg);
+            for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.n; i += gridDim.y * kSplitThreads) gb[pay_of_pixel(geo, i)] = 0.0f;
+        }
         return;
+    }
+    if (tid == 0 && blockIdx.y == 0) {
+        // what the forward multiplies this segment's gradient by: 1 for the unit gradient; in final-gradient
+        // mode the autograd factors of the two means for grad_out = 1, (1 / G) / K with the divisions k_bwd does
+        float sc = 1.0f;
+        if (geo.final_grad) {
+            int K = 0;
+            for (int k = 0; k < geo.C; ++k) K += seg_fg[g * geo.C + k] > 0 ? 1 : 0;
+            if (geo.G > 1) sc = __fdiv_rn(sc, (float)geo.G);
+            if (K > 1) sc = __fdiv_rn(sc, (float)K);
+        }
+        seg_scale[seg] = sc;
     }
     if (force_lsd) {
         if (tid == 0 && blockIdx.y == 0) { nb_out[seg] = 0; fb_flag[seg] = 1u; *fb_any = 1u; }
@@ -295,7 +313,8 @@ static inline size_t part_smem_bytes(int nbk) {
     return sizeof(PartShared) + 2 * pad * sizeof(u32);
 }
 
-template <int TPB>                                  // consecutive tiles of one segment per block (part_tiles_per_block)
+// MI: final gradient with several images per group - the payload index is not the pixel index (Geom)
+template <int TPB, bool MI>                         // TPB consecutive tiles of one segment per block (part_tiles_per_block)
 __global__ void __launch_bounds__(kPThreads, kPBlocksPerSM)
 k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
        const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ ties,
@@ -327,7 +346,6 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     u32 *sm_cnt = sm.arrays;
     u32 *sm_pre = sm.arrays + ((u32)geo.NBK + kPThreads - 1) / kPThreads * kPThreads;
     const u32 n = (u32)geo.n;
-    const size_t seg_off = (size_t)seg * n;
     const u32 *tie = ties + (size_t)seg * kTabBins;         // read through L1: touched only for flagged intervals
     for (u32 tile = tile0; tile < tile0 + tpb; ++tile) {
     const u32 tile_base = tile * (u32)kPTile;
@@ -343,6 +361,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 idx0 = warp * (32 * kPItems) + lane;
     const u32 i0 = tile_base + idx0;
     constexpr u32 kLive = 1u << 29;
+    u32 tile_shift = 0;
     {
         const u32 g = seg / (u32)geo.C, c = seg - g * (u32)geo.C;
         const u32 HW = (u32)geo.HW;
@@ -356,6 +375,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         // the probability is loaded whether or not the pixel turns out to be ignored: the two loads
         // are independent, so a tile waits for one global-memory latency, not two
         const u32 hw_tile = tile_base % HW;
+        // payload index = pixel index + what the images before it add (Geom).  With several images per group
+        // (MI) the host guarantees HW % kPTile == 0: a tile never straddles two images, one value serves it.
+        if (MI) tile_shift = (tile_base / HW) * geo.gstride;
         if (count == (u32)kPTile && hw_tile + (u32)kPTile <= HW) {
             // full tile inside one image (the common case): fixed offsets, no predicates
 #pragma unroll
@@ -379,7 +401,6 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             }
         }
         for (u32 b = tid; b < NB; b += kPThreads) sm_cnt[b] = 0;
-        float *ug = unit_grad ? unit_grad + seg_off : nullptr;
 #pragma unroll
         for (int j = 0; j < kPItems; ++j) {
             const bool fg = code[j] == c;
@@ -388,7 +409,8 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             st[j] = (fg ? kPayloadFg : 0u) | neg;
             if (code[j] != 255u) {
                 if (key[j] != 0xFFFFFFFFu) st[j] |= kLive;
-                else if (ug) ug[i0 + 32 * j] = 0.0f;      // error exactly 0: gradient 0, not sorted
+                else if (unit_grad)       // error exactly 0: gradient 0, not sorted (rare: the address is worked out here)
+                    grad_base_t<MI>(geo, unit_grad, seg)[i0 + 32 * j + tile_shift] = 0.0f;
             }
         }
     }
@@ -489,8 +511,10 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             const u64 v = sm.exch[pos];
             const u32 pl = (u32)v;
             const u32 d = sm_cnt[(pl >> kPB) & 0x7ffu];
-            // global payload: {fg, neg, pixel index in the segment}
-            if (d != kNoDst) dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & kPosMask));
+            // global payload: {fg, neg, payload index of the pixel}
+            if (d != kNoDst) {
+                dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + tile_shift + (pl & kPosMask));
+            }
         }
     }
     }
@@ -539,8 +563,8 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 // One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
 // rk[j] ends as the local rank of element j * kBThreads + tid.
 struct LinMap { u32 lo, R, sh, M; };             // in-bucket linear map (k_plan); R = 0xFFFFFFFF: use the segment's map
-template <int W>
-__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
+template <int W, bool MI>
+__device__ __forceinline__ bool local_ranks(LocalShared &sm, const Geom &geo, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
                                             bool has_ties, const LinMap lm, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
     const u32 lin_lo = lm.lo, lin_R = lm.R, lin_sh = lm.sh, lin_M = lm.M;
     const bool lin = lin_R != 0xFFFFFFFFu;           // block-uniform
@@ -568,7 +592,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
                 d = d < lin_R ? d : lin_R;
                 x16 = __umulhi(d << lin_sh, lin_M);
             } else {
-                x16 = cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu;
+                x16 = cdf_pos(has_ties, (u32)(e >> 32), MI ? pixel_of_pay(geo, (u32)e & kPayloadIdx) : ((u32)e & kPayloadIdx), n, tab, tie, xmax) & 0xffffu;
             }
             const u32 f = x16 >> FSHIFT;
             const u32 sh = (f % FW) * W;
@@ -818,10 +842,12 @@ k_plan(Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb, con
     out[2 * b + 1] = l;
 }
 
+template <bool MI>
 __global__ void __launch_bounds__(kBThreads, RTDA_LOCAL_BLOCKS)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u32 *__restrict__ ties, const uint4 *__restrict__ plan,
-        unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad, u32 *__restrict__ seg_bad) {
+        unsigned long long *__restrict__ seg_sum, float *__restrict__ unit_grad, u32 *__restrict__ seg_bad,
+        const float *__restrict__ seg_scale) {
     extern __shared__ __align__(128) unsigned char local_smem[];
     LocalShared &sm = *reinterpret_cast<LocalShared *>(local_smem);
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -833,6 +859,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     const uint4 pl = plan[2 * (size_t)blockIdx.x + 1];
     const u32 G = seg_fg[seg];
     const u32 nb_raw = nb[seg];
+    const float gscale = seg_scale[seg];             // 1, or the (1 / G) / K of the final gradient (k_split)
     if (!(pa.w & kPlanLive)) return;
     const u32 cnt = pa.x;
     if (tid == 0) {
@@ -863,10 +890,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     mbar_wait(&sm.mbar, 0);
 
     u32 rk[kBItems];
-    if (!local_ranks<4>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+    if (!local_ranks<4, MI>(sm, geo, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+        if (!local_ranks<8, MI>(sm, geo, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
             // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
             // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
             local_sort_all(sm, cnt);
@@ -882,7 +909,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     __syncthreads();
 
     // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
-    float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
+    float *ug = unit_grad ? grad_base_t<MI>(geo, unit_grad, seg) : nullptr;
     LossAcc acc = {0, 0};
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
@@ -902,7 +929,8 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const float err = __uint_as_float(~(u32)(e >> 32));
             flag_nonfinite(~(u32)(e >> 32), seg_bad + seg);
             acc.add(err, gr);
-            if (ug) ug[pay & kPayloadIdx] = (pay & kPayloadNeg) ? gr : -gr;       // err != 0 here
+            // -sgn(fg - p) * g, times the segment's factor (err != 0 here)
+            if (ug) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
         }
     }
     acc.warp_reduce();

@@ -92,11 +92,12 @@ class LovaszOutputs:
                          n_valid=(o + 12, 1, torch.int32), n_present=(o + 16, g, torch.int32),
                          group_loss=(o + 16 + 4 * g, g, torch.float32),
                          class_present=(o + 16 + 8 * g, g * c, torch.int32),
-                         class_loss=(o + 16 + 8 * g + 4 * g * c, g * c, torch.float32))
+                         class_loss=(o + 16 + 8 * g + 4 * g * c, g * c, torch.float32),
+                         applied=(o + 16 + 8 * g + 8 * g * c, 1, torch.float32))
 
     @staticmethod
     def nbytes(groups, classes):
-        return 8 * (4 + 2 * classes) + 16 + 8 * groups + 8 * groups * classes
+        return 8 * (4 + 2 * classes) + 16 + 8 * groups + 8 * groups * classes + 8
 
     def ptr(self, name):
         return self._buf.data_ptr() + self._off[name][0]
@@ -182,8 +183,11 @@ def segment_sort_paths(shape, per_image, stream=None):
     return ws[int(o[16]):int(o[16]) + 4 * groups * c].view(torch.int32).view(groups, c).clone()
 
 
-def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool):
-    """Runs rtda_lovasz_fwd.  probas [B,C,H,W] fp32 contiguous, labels [B,H,W] contiguous."""
+def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool,
+                    exact_backward: bool = False):
+    """Runs rtda_lovasz_fwd.  probas [B,C,H,W] fp32 contiguous, labels [B,H,W] contiguous.  Returns
+    (loss, saved, outs, ws): ``saved`` is (grad [B,C,H,W], None) in final-gradient mode - the forward has
+    written the whole gradient for grad_out = 1 - or (unit [G*C*n], codes) with ``exact_backward``."""
     lib = _lib.load()
     b, c, h, w = probas.shape
     hw = h * w
@@ -196,18 +200,21 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
     _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, int(per_image), _lib.ctypes.byref(nbytes)),
                "rtda_lovasz_workspace_bytes")
     ws = _workspace(dev, stream, nbytes.value)
-    unit = torch.empty(b * c * hw, dtype=torch.float32, device=dev) if need_grad else None
-    codes = torch.empty(b * hw, dtype=torch.uint8, device=dev) if need_grad else None
+    # final-gradient mode where the shape allows it (always with one image per group), else the unit gradient
+    final = need_grad and not exact_backward and bool(lib.rtda_lovasz_final_grad_supported(b, c, hw, int(per_image)))
+    grad = torch.empty((b, c, h, w) if final else (b * c * hw,), dtype=torch.float32, device=dev) if need_grad else None
+    codes = torch.empty(b * hw, dtype=torch.uint8, device=dev) if need_grad and not final else None
     outs = LovaszOutputs(torch.empty(LovaszOutputs.nbytes(groups, c), dtype=torch.uint8, device=dev), groups, c)
     _lib.check(lib.rtda_lovasz_fwd(
         probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
         b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
-        ws.data_ptr(), nbytes.value,
-        unit.data_ptr() if unit is not None else None, codes.data_ptr() if codes is not None else None,
+        ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL if final else _lib.GRAD_UNIT,
+        grad.data_ptr() if grad is not None else None, codes.data_ptr() if codes is not None else None,
+        outs.ptr("applied") if final else None,
         outs.ptr("loss"), outs.ptr("class_loss"),
         outs.ptr("class_present"), outs.ptr("n_present"), outs.ptr("group_loss"), outs.ptr("label_errors"),
         outs.ptr("packed"), stream), "rtda_lovasz_fwd")
-    return outs.loss, (unit, codes), outs, ws
+    return outs.loss, (grad, codes), outs, ws
 
 
 _pending_reduce = {}   # device index -> LovaszOutputs whose asynchronous all-reduce may still be in flight
@@ -219,14 +226,16 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
     packed partials and returns the global mean; the backward needs no collective."""
 
     @staticmethod
-    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None, grad_reduction="sum"):
+    def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None, grad_reduction="sum",
+                exact_backward=False):
         need_grad = bool(ctx.needs_input_grad[0])
-        loss, (unit, codes), outs, _ws = _forward_native(probas, labels, ignore, per_image, need_grad)
+        loss, (grad, codes), outs, ws = _forward_native(probas, labels, ignore, per_image, need_grad, exact_backward)
         if holder is not None:
             holder.append(outs)
         ctx.shape = tuple(probas.shape)
         ctx.per_image = per_image
         ctx.shard_scale = None
+        ctx.final = need_grad and codes is None          # the forward wrote the finished gradient (no class codes kept)
         if shard_group is not None:
             import torch.distributed as dist
 
@@ -251,27 +260,39 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
                 _pending_reduce[probas.device.index] = outs
                 ctx.shard_scale = float(probas.size(0)) * dscale / float(global_images)
         if need_grad:
-            ctx.save_for_backward(unit, codes, outs.class_present, outs.n_present)
+            if ctx.final:
+                ctx.ws = ws                              # the in-place backward uses one counter of this workspace
+                ctx.save_for_backward(grad, outs._view("applied"))
+            else:
+                ctx.save_for_backward(grad, codes, outs.class_present, outs.n_present)
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        unit, codes, present, n_present = ctx.saved_tensors
         b, c, h, w = ctx.shape
         lib = _lib.load()
-        dev = unit.device
+        dev = ctx.saved_tensors[0].device
         go = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
         if ctx.shard_scale is not None:
             go = go * ctx.shard_scale
-        grad = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
+        if ctx.final:
+            # the forward wrote the whole gradient for grad_out = 1: nothing to do for the plain backward(),
+            # one in-place multiplication otherwise (exact for power-of-two factors)
+            grad, applied = ctx.saved_tensors
+            _lib.check(lib.rtda_lovasz_bwd_inplace(
+                go.data_ptr(), grad.data_ptr(), applied.data_ptr(), ctx.ws.data_ptr(), b, c, h * w,
+                torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd_inplace")
+            return grad, None, None, None, None, None, None, None, None
+        unit, codes, present, n_present = ctx.saved_tensors
+        grad = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
         _lib.check(lib.rtda_lovasz_bwd(
             go.data_ptr(), unit.data_ptr(), codes.data_ptr(), present.data_ptr(), n_present.data_ptr(),
             b, c, h * w, int(ctx.per_image), grad.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
-        return grad, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None
 
 
 def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
@@ -296,7 +317,7 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
 
 def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
                    validate_labels=False, return_outputs=False, shard_group=None, global_images=None,
-                   grad_reduction="sum"):
+                   grad_reduction="sum", exact_backward=False):
     """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
     computes, lovasz_loss.py:185-200).
 
@@ -310,6 +331,13 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
     The local gradient is scaled by ``B_local / B_global`` so that the SUM of the ranks' parameter
     gradients is the single-device gradient; ``grad_reduction="mean"`` multiplies it by the world size
     for DistributedDataParallel, which averages gradients.
+
+    Backward: the forward's sort kernels write the finished gradient for ``grad_out = 1`` straight into the
+    NCHW buffer autograd receives; ``loss.backward()`` then launches one kernel that finds nothing to do.  Any
+    other ``grad_out`` (a loss weight, an AMP loss scale) multiplies that buffer in place: bit-identical to
+    the reference's fp32 sequence ``(grad_out / G) / K * g`` when the factor is a power of two, within 3 ulp
+    of it otherwise.  ``exact_backward=True`` keeps the unit gradient and runs the separate backward kernel,
+    bit-exact for every ``grad_out`` (one more pass over the gradient).
     """
     if classes not in ("present", "all"):
         raise ValueError("classes must be 'present' or 'all'")
@@ -322,7 +350,7 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
         raise ValueError("only per_image=True shards over ranks (global mode needs one sort over all pixels)")
     holder = []
     loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group, global_images,
-                                        grad_reduction)
+                                        grad_reduction, bool(exact_backward))
     outs = holder[0]
     if validate_labels:
         bad = int(outs.label_errors.item())
@@ -379,12 +407,14 @@ class LovaszSoftmax(nn.Module):
     main_adversarial.py:233-237).  Stateless; ``per_image``,
     ``validate_labels`` and ``capture`` (CUDA-graph replay, graphed.py) are additions (see the module docstring)."""
 
-    def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False, capture=False):
+    def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False, capture=False,
+                 exact_backward=False):
         super().__init__()
         self.reduction = reduction
         self.ignore = ignore
         self.per_image = per_image
         self.validate_labels = validate_labels
+        self.exact_backward = exact_backward
         self.last_outputs = None
         # capture=True: one CUDA graph of the forward and one of the backward per input shape (graphed.py)
         if capture and validate_labels:
@@ -394,7 +424,7 @@ class LovaszSoftmax(nn.Module):
             from .graphed import GraphedCriterion
 
             self._graphed = GraphedCriterion(lambda p, l: (lovasz_softmax(p, l, classes="present", per_image=self.per_image,
-                                                                          ignore=self.ignore),))
+                                                                          ignore=self.ignore, exact_backward=self.exact_backward),))
 
     def prob_flatten(self, input, target):
         """[B,C,H,W] -> [B*H*W, C] and [B,H,W] -> [B*H*W] (lovasz_loss.py:93-120)."""
@@ -411,8 +441,8 @@ class LovaszSoftmax(nn.Module):
             self.last_outputs = None          # the side outputs live in the graph's static buffers
             return loss
         loss, outs = lovasz_softmax(probas, labels, classes="present", per_image=self.per_image,
-                                    ignore=self.ignore, validate_labels=self.validate_labels,
-                                    return_outputs=True) if probas.numel() else (lovasz_softmax(probas, labels), None)
+                                    ignore=self.ignore, validate_labels=self.validate_labels, return_outputs=True,
+                                    exact_backward=self.exact_backward) if probas.numel() else (lovasz_softmax(probas, labels), None)
         self.last_outputs = outs
         return loss
 

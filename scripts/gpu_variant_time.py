@@ -23,7 +23,7 @@ def main():
     name = os.path.basename(os.environ.get("RTDA_LIB_PATH", "default"))
     n_sets = 3 if wl != "c3" else 2
     sets = [synthetic.confident_case(b, h, w, seed=1234 + 1000 * i, device="cuda") for i in range(n_sets)]
-    crit = rtda.LovaszSoftmax(ignore=255, per_image=per_image)
+    crit = rtda.LovaszSoftmax(ignore=255, per_image=per_image, exact_backward=bool(int(os.environ.get("RTDA_EXACT_BACKWARD", "0"))))
     graphs = []
     side = torch.cuda.Stream()
     for p, l in sets:

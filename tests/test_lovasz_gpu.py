@@ -28,16 +28,30 @@ def sort_path(request):
     rtda.set_sort_path("bucket")
 
 
+@pytest.fixture(autouse=True, params=["final", "exact"])
+def backward_mode(request):
+    """... and with both forms of the backward: the forward's kernels writing the finished gradient for
+    grad_out = 1 (default; other factors scale it in place), and the unit gradient + separate backward kernel
+    (exact_backward=True)."""
+    global EXACT_BACKWARD
+    EXACT_BACKWARD = request.param == "exact"
+    yield request.param
+    EXACT_BACKWARD = False
+
+
+EXACT_BACKWARD = False
+
+
 def run_cuda(probas, labels, ignore=255, per_image=False, grad_out=None, label_dtype=None, module=True):
     p = torch.as_tensor(probas).cuda().requires_grad_(True)
     l = torch.as_tensor(labels).cuda()
     if label_dtype is not None:
         l = l.to(label_dtype)
     if module:
-        crit = rtda.LovaszSoftmax(ignore=ignore, per_image=per_image)
+        crit = rtda.LovaszSoftmax(ignore=ignore, per_image=per_image, exact_backward=EXACT_BACKWARD)
         loss = crit(p, l)
     else:
-        loss = rtda.lovasz_softmax(p, l, per_image=per_image, ignore=ignore)
+        loss = rtda.lovasz_softmax(p, l, per_image=per_image, ignore=ignore, exact_backward=EXACT_BACKWARD)
     assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.is_cuda
     (loss if grad_out is None else loss * grad_out).backward()
     torch.cuda.synchronize()
@@ -158,6 +172,41 @@ def test_grad_out_scales_exactly_like_autograd():
     probas, labels = synthetic.diffuse_case(2, 32, 48, seed=22)
     for per_image in (False, True):
         assert_matches_oracle(probas.numpy(), labels.numpy(), 255, per_image, grad_out=32768.0 * 0.5, tag="scaled")
+
+
+def test_grad_out_that_is_not_a_power_of_two():
+    """The in-place backward multiplies the finished gradient by grad_out: one more rounding than the
+    reference's ((grad_out / G) / K) * g for factors that are not powers of two - a few ulp apart (one per
+    factor that is rounded in a different order), far inside the 1e-5 bar; exact_backward=True is bit-exact
+    for every factor."""
+    probas, labels = synthetic.confident_case(2, 48, 64, seed=24)
+    for go in (0.3, 3.0, 1.0 / 3.0):
+        for per_image in (False, True):
+            want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, per_image, grad_out=go)
+            _, grad = run_cuda(probas, labels, 255, per_image, grad_out=go)
+            if EXACT_BACKWARD:
+                assert np.array_equal(grad, want["grad"])
+            else:
+                ulp = np.spacing(np.abs(want["grad"]).astype(np.float32))
+                assert (np.abs(grad - want["grad"]) <= 3 * ulp).all()
+                assert np.array_equal(grad == 0, want["grad"] == 0)
+
+
+def test_backward_twice_and_grad_out_one():
+    """retain_graph: the second backward of the final-gradient mode finds the buffer already scaled
+    (applied_scale) and a different factor rescales it; the plain backward leaves it untouched."""
+    probas, labels = synthetic.confident_case(1, 40, 56, seed=25)
+    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, False)
+    p = probas.cuda().requires_grad_(True)
+    loss = rtda.LovaszSoftmax(ignore=255, exact_backward=EXACT_BACKWARD)(p, labels.cuda())
+    (g1,) = torch.autograd.grad(loss, p, retain_graph=True)
+    g1 = g1.clone()
+    (g2,) = torch.autograd.grad(loss, p, torch.tensor(4.0, device="cuda"), retain_graph=True)
+    g2 = g2.clone()
+    (g3,) = torch.autograd.grad(loss, p, torch.tensor(0.5, device="cuda"))
+    assert np.array_equal(g1.cpu().numpy(), want["grad"])
+    assert np.array_equal(g2.cpu().numpy(), want["grad"] * np.float32(4.0))
+    assert np.array_equal(g3.cpu().numpy(), want["grad"] * np.float32(0.5))
 
 
 def test_half_precision_inputs_and_autocast():

@@ -29,7 +29,7 @@ def sort_path(request):
     rtda.set_sort_path("bucket")
 
 
-def raw_fwd_bwd(probas, labels, per_image, fill, grad_out=1.0, logits=None):
+def raw_fwd_bwd(probas, labels, per_image, fill, grad_out=1.0, logits=None, final=False):
     """Calls the C ABI directly with every output buffer and the workspace pre-filled with `fill` bytes.
     Returns the bytes of (loss, class_loss, present, n_present, grad)."""
     lib = _lib.load()
@@ -52,9 +52,17 @@ def raw_fwd_bwd(probas, labels, per_image, fill, grad_out=1.0, logits=None):
     grad = buf(4 * b * c * hw, torch.float32)
     go = torch.tensor([grad_out], dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    if logits is None:
+    if logits is None and final:
+        # final-gradient mode: the forward writes every element of the NCHW gradient; the backward scales in place
         _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, int(per_image),
-                                       ws.data_ptr(), nbytes.value, unit.data_ptr(), codes.data_ptr(), outs.ptr("loss"),
+                                       ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL, grad.data_ptr(), None, outs.ptr("applied"),
+                                       outs.ptr("loss"), outs.ptr("class_loss"), outs.ptr("class_present"), outs.ptr("n_present"),
+                                       outs.ptr("group_loss"), outs.ptr("label_errors"), outs.ptr("packed"), st), "fwd")
+        _lib.check(lib.rtda_lovasz_bwd_inplace(go.data_ptr(), grad.data_ptr(), outs.ptr("applied"), ws.data_ptr(), b, c, hw, st), "bwd_inplace")
+        extra = ()
+    elif logits is None:
+        _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, int(per_image),
+                                       ws.data_ptr(), nbytes.value, _lib.GRAD_UNIT, unit.data_ptr(), codes.data_ptr(), None, outs.ptr("loss"),
                                        outs.ptr("class_loss"), outs.ptr("class_present"), outs.ptr("n_present"),
                                        outs.ptr("group_loss"), outs.ptr("label_errors"), outs.ptr("packed"), st), "fwd")
         _lib.check(lib.rtda_lovasz_bwd(go.data_ptr(), unit.data_ptr(), codes.data_ptr(), outs.ptr("class_present"),
@@ -77,7 +85,7 @@ def raw_fwd_bwd(probas, labels, per_image, fill, grad_out=1.0, logits=None):
 
 
 CASES = {
-    "conf_global": lambda: synthetic.confident_case(2, 96, 160, seed=3) + (False,),
+    "conf_global": lambda: synthetic.confident_case(2, 64, 192, seed=3) + (False,),       # HW % 4096 == 0: final-gradient mode with 2 images per group
     "conf_per_image_odd": lambda: synthetic.confident_case(3, 33, 47, seed=4) + (True,),
     "absent_classes_and_empty_image": lambda: _absent_case(),
     "saturated_ties": lambda: _saturated_case(),
@@ -98,15 +106,21 @@ def _saturated_case():
     return torch.softmax(lg, 1), lab, False
 
 
+@pytest.mark.parametrize("final", [True, False], ids=["final_grad", "unit_grad"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_poisoned_buffers_give_identical_bits(case, sort_path):
+def test_poisoned_buffers_give_identical_bits(case, final, sort_path):
+    """Both gradient modes of the forward.  In final-gradient mode the forward itself must write EVERY element
+    of the gradient (zeros at ignored pixels, in absent classes, in images without a valid pixel)."""
     probas, labels, per_image = CASES[case]()
-    clean = raw_fwd_bwd(probas, labels, per_image, 0x00, grad_out=0.75)
+    if final and not _lib.load().rtda_lovasz_final_grad_supported(probas.size(0), probas.size(1), probas.size(2) * probas.size(3), int(per_image)):
+        pytest.skip("final-gradient mode needs HW % 4096 == 0 with several images per group")
+    go = 0.5 if final else 0.75                 # the in-place backward is exact for powers of two
+    clean = raw_fwd_bwd(probas, labels, per_image, 0x00, grad_out=go, final=final)
     for fill in (0xFF, 0x7F):                  # 0xFFFFFFFF = NaN, 0x7F7F7F7F = 3.4e38: any read of it shows
-        dirty = raw_fwd_bwd(probas, labels, per_image, fill, grad_out=0.75)
+        dirty = raw_fwd_bwd(probas, labels, per_image, fill, grad_out=go, final=final)
         for name, a, b in zip(("loss", "class_loss", "present", "n_present", "packed", "grad"), clean, dirty):
             assert a == b, f"{case}: {name} depends on the initial contents of a buffer (fill {fill:#x})"
-    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, per_image, grad_out=0.75)
+    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, per_image, grad_out=go)
     assert np.array_equal(np.frombuffer(clean[5], np.float32).reshape(probas.shape), want["grad"])
 
 
