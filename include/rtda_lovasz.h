@@ -120,9 +120,10 @@ int rtda_lovasz_set_sort_path(int path);
  */
 #define RTDA_GRAD_UNIT 0
 #define RTDA_GRAD_FINAL 1
-/* 1 when RTDA_GRAD_FINAL is available for this shape: always with one image per group (per_image, or B = 1);
- * with several images per group it needs HW % 4096 == 0 and B*C*HW < 2^30 (rtda_lovasz_fwd returns
- * RTDA_E_RANGE otherwise; use RTDA_GRAD_UNIT + rtda_lovasz_bwd there). */
+/* 1 when RTDA_GRAD_FINAL is available for this shape: one image per group (per_image, or B = 1), where the
+ * NCHW layout [B][C][HW] is the segment layout [G][C][n].  With several images per group rtda_lovasz_fwd
+ * returns RTDA_E_RANGE for it (scattering into B planes per class measured slower than the contiguous unit
+ * gradient + rtda_lovasz_bwd): use RTDA_GRAD_UNIT there. */
 int rtda_lovasz_final_grad_supported(int64_t B, int C, int64_t HW, int per_image);
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,

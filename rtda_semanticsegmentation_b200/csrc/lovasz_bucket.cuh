@@ -141,8 +141,8 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         if (geo.final_grad && grad) {
             // the final gradient has no separate zero-filling pass: the planes of an absent class are zeroed here
             // (ignored pixels: k_prep; everything else is written by the kernels that sort the segment)
-            float *gb = grad_base(geo, grad, seg);
-            for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.n; i += gridDim.y * kSplitThreads) gb[pay_of_pixel(geo, i)] = 0.0f;
+            float *gb = grad + (size_t)seg * (size_t)geo.n;      // one image per group: [B][C][HW] is [G][C][n]
+            for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.n; i += gridDim.y * kSplitThreads) gb[i] = 0.0f;
         }
         return;
     }
@@ -313,8 +313,7 @@ static inline size_t part_smem_bytes(int nbk) {
     return sizeof(PartShared) + 2 * pad * sizeof(u32);
 }
 
-// MI: final gradient with several images per group - the payload index is not the pixel index (Geom)
-template <int TPB, bool MI>                         // TPB consecutive tiles of one segment per block (part_tiles_per_block)
+template <int TPB>                                  // consecutive tiles of one segment per block (part_tiles_per_block)
 __global__ void __launch_bounds__(kPThreads, kPBlocksPerSM)
 k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes, Geom geo,
        const u32 *__restrict__ seg_fg, const u32 *__restrict__ table, const u32 *__restrict__ ties,
@@ -361,7 +360,6 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     const u32 idx0 = warp * (32 * kPItems) + lane;
     const u32 i0 = tile_base + idx0;
     constexpr u32 kLive = 1u << 29;
-    u32 tile_shift = 0;
     {
         const u32 g = seg / (u32)geo.C, c = seg - g * (u32)geo.C;
         const u32 HW = (u32)geo.HW;
@@ -375,9 +373,6 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         // the probability is loaded whether or not the pixel turns out to be ignored: the two loads
         // are independent, so a tile waits for one global-memory latency, not two
         const u32 hw_tile = tile_base % HW;
-        // payload index = pixel index + what the images before it add (Geom).  With several images per group
-        // (MI) the host guarantees HW % kPTile == 0: a tile never straddles two images, one value serves it.
-        if (MI) tile_shift = (tile_base / HW) * geo.gstride;
         if (count == (u32)kPTile && hw_tile + (u32)kPTile <= HW) {
             // full tile inside one image (the common case): fixed offsets, no predicates
 #pragma unroll
@@ -410,7 +405,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             if (code[j] != 255u) {
                 if (key[j] != 0xFFFFFFFFu) st[j] |= kLive;
                 else if (unit_grad)       // error exactly 0: gradient 0, not sorted (rare: the address is worked out here)
-                    grad_base_t<MI>(geo, unit_grad, seg)[i0 + 32 * j + tile_shift] = 0.0f;
+                    unit_grad[(size_t)seg * n + i0 + 32 * j] = 0.0f;
             }
         }
     }
@@ -511,9 +506,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             const u64 v = sm.exch[pos];
             const u32 pl = (u32)v;
             const u32 d = sm_cnt[(pl >> kPB) & 0x7ffu];
-            // global payload: {fg, neg, payload index of the pixel}
+            // global payload: {fg, neg, pixel index in the segment}
             if (d != kNoDst) {
-                dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + tile_shift + (pl & kPosMask));
+                dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & kPosMask));
             }
         }
     }
@@ -563,8 +558,8 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 // One attempt with W-bit counters.  Returns false (block-uniform) when a counter overflowed.
 // rk[j] ends as the local rank of element j * kBThreads + tid.
 struct LinMap { u32 lo, R, sh, M; };             // in-bucket linear map (k_plan); R = 0xFFFFFFFF: use the segment's map
-template <int W, bool MI>
-__device__ __forceinline__ bool local_ranks(LocalShared &sm, const Geom &geo, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
+template <int W>
+__device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
                                             bool has_ties, const LinMap lm, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
     const u32 lin_lo = lm.lo, lin_R = lm.R, lin_sh = lm.sh, lin_M = lm.M;
     const bool lin = lin_R != 0xFFFFFFFFu;           // block-uniform
@@ -592,7 +587,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const Geom &geo, co
                 d = d < lin_R ? d : lin_R;
                 x16 = __umulhi(d << lin_sh, lin_M);
             } else {
-                x16 = cdf_pos(has_ties, (u32)(e >> 32), MI ? pixel_of_pay(geo, (u32)e & kPayloadIdx) : ((u32)e & kPayloadIdx), n, tab, tie, xmax) & 0xffffu;
+                x16 = cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu;
             }
             const u32 f = x16 >> FSHIFT;
             const u32 sh = (f % FW) * W;
@@ -842,7 +837,6 @@ k_plan(Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb, con
     out[2 * b + 1] = l;
 }
 
-template <bool MI>
 __global__ void __launch_bounds__(kBThreads, RTDA_LOCAL_BLOCKS)
 k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_fg, const u32 *__restrict__ nb,
         const u32 *__restrict__ table, const u32 *__restrict__ ties, const uint4 *__restrict__ plan,
@@ -890,10 +884,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     mbar_wait(&sm.mbar, 0);
 
     u32 rk[kBItems];
-    if (!local_ranks<4, MI>(sm, geo, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+    if (!local_ranks<4>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8, MI>(sm, geo, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+        if (!local_ranks<8>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
             // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
             // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
             local_sort_all(sm, cnt);
@@ -909,7 +903,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     __syncthreads();
 
     // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
-    float *ug = unit_grad ? grad_base_t<MI>(geo, unit_grad, seg) : nullptr;
+    float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
     LossAcc acc = {0, 0};
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import rtda_semanticsegmentation_b200 as rtda  # noqa: E402
 from rtda_semanticsegmentation_b200 import _lib, synthetic  # noqa: E402
 
-SHAPES = {"c1": (1, 512, 1024, False), "c2": (4, 512, 1024, False), "c3": (16, 720, 1280, True), "c5": (8, 512, 1024, False)}
+SHAPES = {"c1": (1, 512, 1024, False), "c2": (4, 512, 1024, False), "c2pi": (4, 512, 1024, True), "c3": (16, 720, 1280, True), "c5": (8, 512, 1024, False)}
 
 
 def main():
@@ -71,7 +71,7 @@ def main():
     fb = int(rtda.segment_sort_paths((b, 19, h, w), per_image).sum())
     pick = {k: v[0] / max(v[1], 1) * 1e3 for k, v in st.items()}
     print(f"{wl} {name:12s} best {best:.4f} mean {tot / 3:.4f} ms/step  {b * h * w / best / 1e3:.0f} Mpix/s  fb {fb}  loss_bits {lbits:#x} grad_csum {csum}  "
-          f"split {pick.get('k_split', 0):.1f} plan {pick.get('k_plan', 0):.1f} part {pick.get('k_part', 0):.1f} local {pick.get('k_local', 0):.1f} bwd {pick.get('k_bwd', 0):.1f} us", flush=True)
+          f"prep {pick.get('k_prep', 0):.1f} fin {pick.get('k_finalize', 0):.1f} split {pick.get('k_split', 0):.1f} plan {pick.get('k_plan', 0):.1f} part {pick.get('k_part', 0):.1f} local {pick.get('k_local', 0):.1f} bwd {pick.get('k_bwd', 0):.1f} us", flush=True)
 
 
 if __name__ == "__main__":
