@@ -905,6 +905,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
     float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
     LossAcc acc = {0, 0};
+    u32 eb_max = 0;
 #pragma unroll
     for (int j = 0; j < kBItems; ++j) {
         const u32 idx = j * kBThreads + tid;
@@ -921,12 +922,13 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
             const float gr = __fsub_rn(jac, jprev);
             const float err = __uint_as_float(~(u32)(e >> 32));
-            flag_nonfinite(~(u32)(e >> 32), seg_bad + seg);
+            eb_max = ~(u32)(e >> 32) > eb_max ? ~(u32)(e >> 32) : eb_max;
             acc.add(err, gr);
             // -sgn(fg - p) * g, times the segment's factor (err != 0 here)
             if (ug) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
         }
     }
+    flag_nonfinite(eb_max, seg_bad + seg);         // (a NaN's bit pattern compares above every finite one)
     acc.warp_reduce();
     if (lane == 0) { sm.red[0][warp] = acc.a; sm.red[1][warp] = acc.b; }
     __syncthreads();
