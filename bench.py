@@ -618,7 +618,9 @@ def main():
     def criterion(kind, per_img):
         if kind == "fused":
             return rtda.HybridCELovasz(ignore=255, lovasz_weight=0.5, per_image=per_img)
-        lov = rtda.LovaszSoftmax(ignore=255, per_image=per_img)
+        # N > 1: the step's loss is this rank's share 1/world of the global mean; the forward is told so and writes the
+        # gradient for that factor (what dist.lovasz_softmax_sharded(global_images=...) does), the backward is a no-op
+        lov = rtda.LovaszSoftmax(ignore=255, per_image=per_img, grad_out_hint=(1.0 / world) if (world > 1 and kind == "none") else 1.0)
         return Unfused(lov) if kind == "unfused" else lov
 
     sets, set_bytes = make_sets(args.workload, imgs, H, W, rank, dev, args.hybrid != "none", args.distribution)

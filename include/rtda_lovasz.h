@@ -87,11 +87,12 @@ int rtda_lovasz_debug_layout(int64_t B, int C, int64_t HW, int per_image, size_t
 int rtda_lovasz_set_sort_path(int path);
 
 /* Where the forward leaves the gradient (`grad_mode`):
- *   RTDA_GRAD_FINAL  `grad` [B][C][HW] fp32 (the caller's NCHW layout) receives d(loss)/d(probas) for
- *                    grad_out = 1, complete: the 1/K and 1/G factors of the two means applied with the same
+ *   RTDA_GRAD_FINAL  `grad` [B][C][HW] fp32 (the caller's NCHW layout) receives d(loss * h)/d(probas) for
+ *                    h = grad_out_hint - the grad_out the caller expects to pass to the backward: 1 for a plain
+ *                    loss.backward(), the loss weight, the share of a batch sharded over ranks - complete: the 1/K and 1/G factors of the two means applied with the same
  *                    fp32 divisions autograd performs, zeros at ignored pixels and in absent classes.  The
  *                    sort kernels write it directly; there is no second pass over it.  The backward is
- *                    rtda_lovasz_bwd_inplace: nothing to do for grad_out = 1, one in-place multiplication
+ *                    rtda_lovasz_bwd_inplace: nothing to do for grad_out = h, one in-place multiplication
  *                    otherwise.  `applied_scale` [1] fp32 records which grad_out the buffer currently holds.
  *   RTDA_GRAD_UNIT   `grad` [G][C][n] fp32, n = B*HW/G, receives the unit gradient -g_rank * sgn(fg - p)
  *                    before the 1/K and 1/G factors; rows of absent classes and ignored pixels are NOT
@@ -101,7 +102,7 @@ int rtda_lovasz_set_sort_path(int path);
  *   grad          see above; may be NULL (loss only, e.g. under torch.no_grad()).
  *   codes         [B*HW] u8, 4-byte aligned when HW % 4 == 0: the class of every pixel, 255 = ignored or
  *                 out of range; required with RTDA_GRAD_UNIT (its backward reads it), else may be NULL.
- *   applied_scale [1] fp32, set to 1; required with RTDA_GRAD_FINAL, else may be NULL.
+ *   applied_scale [1] fp32, set to grad_out_hint; required with RTDA_GRAD_FINAL, else may be NULL.
  *   loss          [1]    fp32  the scalar loss (0 when nothing is valid)
  *   class_loss    [G][C] fp32  per-class Lovasz losses (0 where absent)
  *   class_present [G][C] i32   1 where the class has a valid foreground pixel
@@ -127,7 +128,7 @@ int rtda_lovasz_set_sort_path(int path);
 int rtda_lovasz_final_grad_supported(int64_t B, int C, int64_t HW, int per_image);
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,
-                    void *ws, size_t ws_bytes, int grad_mode,
+                    void *ws, size_t ws_bytes, int grad_mode, float grad_out_hint,
                     float *grad, uint8_t *codes, float *applied_scale, float *loss, float *class_loss,
                     int32_t *class_present, int32_t *n_present, float *group_loss,
                     int32_t *label_errors, double *packed, void *stream);

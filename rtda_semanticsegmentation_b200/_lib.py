@@ -29,7 +29,7 @@ SIGNATURES = {
     "rtda_lovasz_workspace_bytes": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "rtda_lovasz_debug_layout": (_int, [_i64, _int, _i64, _int, ctypes.POINTER(_sz)]),
     "rtda_lovasz_set_sort_path": (_int, [_int]),
-    "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz, _int,
+    "rtda_lovasz_fwd": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _int, _int, _vp, _sz, _int, ctypes.c_float,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rtda_lovasz_final_grad_supported": (_int, [_i64, _int, _i64, _int]),
     "rtda_lovasz_bwd_inplace": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _vp]),

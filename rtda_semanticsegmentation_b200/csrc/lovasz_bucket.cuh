@@ -140,7 +140,6 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         if (tid == 0 && blockIdx.y == 0) nb_out[seg] = 0;
         if (geo.final_grad && grad) {
             // the final gradient has no separate zero-filling pass: the planes of an absent class are zeroed here
-            // (ignored pixels: k_prep; everything else is written by the kernels that sort the segment)
             float *gb = grad + (size_t)seg * (size_t)geo.n;      // one image per group: [B][C][HW] is [G][C][n]
             for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.n; i += gridDim.y * kSplitThreads) gb[i] = 0.0f;
         }
@@ -148,9 +147,10 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     }
     if (tid == 0 && blockIdx.y == 0) {
         // what the forward multiplies this segment's gradient by: 1 for the unit gradient; in final-gradient
-        // mode the autograd factors of the two means for grad_out = 1, (1 / G) / K with the divisions k_bwd does
+        // mode the autograd factors of the two means, (grad_out / G) / K with the divisions k_bwd does
         float sc = 1.0f;
         if (geo.final_grad) {
+            sc = geo.grad_hint;                    // the grad_out the gradient is written for (1 unless the caller said otherwise)
             int K = 0;
             for (int k = 0; k < geo.C; ++k) K += seg_fg[g * geo.C + k] > 0 ? 1 : 0;
             if (geo.G > 1) sc = __fdiv_rn(sc, (float)geo.G);

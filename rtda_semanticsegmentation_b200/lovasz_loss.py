@@ -184,7 +184,7 @@ def segment_sort_paths(shape, per_image, stream=None):
 
 
 def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_image: bool, need_grad: bool,
-                    exact_backward: bool = False):
+                    exact_backward: bool = False, grad_out_hint: float = 1.0):
     """Runs rtda_lovasz_fwd.  probas [B,C,H,W] fp32 contiguous, labels [B,H,W] contiguous.  Returns
     (loss, saved, outs, ws): ``saved`` is (grad [B,C,H,W], None) in final-gradient mode - the forward has
     written the whole gradient for grad_out = 1 - or (unit [G*C*n], codes) with ``exact_backward``."""
@@ -208,7 +208,7 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
     _lib.check(lib.rtda_lovasz_fwd(
         probas.data_ptr(), labels.data_ptr(), _lib.label_kind(labels.dtype),
         b, c, hw, 0 if ignore is None else int(ignore), int(ignore is not None), int(per_image),
-        ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL if final else _lib.GRAD_UNIT,
+        ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL if final else _lib.GRAD_UNIT, float(grad_out_hint),
         grad.data_ptr() if grad is not None else None, codes.data_ptr() if codes is not None else None,
         outs.ptr("applied") if final else None,
         outs.ptr("loss"), outs.ptr("class_loss"),
@@ -227,9 +227,16 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, probas, labels, ignore, per_image, holder, shard_group, global_images=None, grad_reduction="sum",
-                exact_backward=False):
+                exact_backward=False, grad_out_hint=1.0):
         need_grad = bool(ctx.needs_input_grad[0])
-        loss, (grad, codes), outs, ws = _forward_native(probas, labels, ignore, per_image, need_grad, exact_backward)
+        hint = float(grad_out_hint)
+        if shard_group is not None and global_images is not None:
+            # the factor of this rank's slice is known on the host: the forward writes the gradient for it
+            import torch.distributed as dist
+
+            grp = None if shard_group is True else shard_group
+            hint *= float(probas.size(0)) * (float(dist.get_world_size(grp)) if grad_reduction == "mean" else 1.0) / float(global_images)
+        loss, (grad, codes), outs, ws = _forward_native(probas, labels, ignore, per_image, need_grad, exact_backward, hint)
         if holder is not None:
             holder.append(outs)
         ctx.shape = tuple(probas.shape)
@@ -285,14 +292,14 @@ class _LovaszSoftmaxFunction(torch.autograd.Function):
             _lib.check(lib.rtda_lovasz_bwd_inplace(
                 go.data_ptr(), grad.data_ptr(), applied.data_ptr(), ctx.ws.data_ptr(), b, c, h * w,
                 torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd_inplace")
-            return grad, None, None, None, None, None, None, None, None
+            return grad, None, None, None, None, None, None, None, None, None
         unit, codes, present, n_present = ctx.saved_tensors
         grad = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
         _lib.check(lib.rtda_lovasz_bwd(
             go.data_ptr(), unit.data_ptr(), codes.data_ptr(), present.data_ptr(), n_present.data_ptr(),
             b, c, h * w, int(ctx.per_image), grad.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream), "rtda_lovasz_bwd")
-        return grad, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None
 
 
 def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
@@ -317,7 +324,7 @@ def _as_kernel_inputs(probas: torch.Tensor, labels: torch.Tensor):
 
 def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=None,
                    validate_labels=False, return_outputs=False, shard_group=None, global_images=None,
-                   grad_reduction="sum", exact_backward=False):
+                   grad_reduction="sum", exact_backward=False, grad_out_hint=1.0):
     """Multi-class Lovasz-Softmax loss (Berman signature; what LovaszSoftmax.forward
     computes, lovasz_loss.py:185-200).
 
@@ -336,7 +343,10 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
     NCHW buffer autograd receives; ``loss.backward()`` then launches one kernel that finds nothing to do.  Any
     other ``grad_out`` (a loss weight, an AMP loss scale) multiplies that buffer in place: bit-identical to
     the reference's fp32 sequence ``(grad_out / G) / K * g`` when the factor is a power of two, within 3 ulp
-    of it otherwise.  ``exact_backward=True`` keeps the unit gradient and runs the separate backward kernel,
+    of it otherwise.  ``grad_out_hint`` names the ``grad_out`` the caller expects to pass (the weight of this loss in
+    the total, e.g. 0.5): the forward then writes the gradient for THAT factor and the backward again has nothing
+    to do; a wrong hint only costs the multiplication.  The factor of a sharded batch with ``global_images`` is
+    folded in automatically.  ``exact_backward=True`` keeps the unit gradient and runs the separate backward kernel,
     bit-exact for every ``grad_out`` (one more pass over the gradient).
     """
     if classes not in ("present", "all"):
@@ -350,7 +360,7 @@ def lovasz_softmax(probas, labels, classes="present", per_image=False, ignore=No
         raise ValueError("only per_image=True shards over ranks (global mode needs one sort over all pixels)")
     holder = []
     loss = _LovaszSoftmaxFunction.apply(probas, labels, ignore, bool(per_image), holder, shard_group, global_images,
-                                        grad_reduction, bool(exact_backward))
+                                        grad_reduction, bool(exact_backward), float(grad_out_hint))
     outs = holder[0]
     if validate_labels:
         bad = int(outs.label_errors.item())
@@ -408,13 +418,14 @@ class LovaszSoftmax(nn.Module):
     ``validate_labels`` and ``capture`` (CUDA-graph replay, graphed.py) are additions (see the module docstring)."""
 
     def __init__(self, reduction="mean", ignore=None, per_image=False, validate_labels=False, capture=False,
-                 exact_backward=False):
+                 exact_backward=False, grad_out_hint=1.0):
         super().__init__()
         self.reduction = reduction
         self.ignore = ignore
         self.per_image = per_image
         self.validate_labels = validate_labels
         self.exact_backward = exact_backward
+        self.grad_out_hint = grad_out_hint     # the weight this loss gets in the total (see lovasz_softmax)
         self.last_outputs = None
         # capture=True: one CUDA graph of the forward and one of the backward per input shape (graphed.py)
         if capture and validate_labels:
@@ -424,7 +435,8 @@ class LovaszSoftmax(nn.Module):
             from .graphed import GraphedCriterion
 
             self._graphed = GraphedCriterion(lambda p, l: (lovasz_softmax(p, l, classes="present", per_image=self.per_image,
-                                                                          ignore=self.ignore, exact_backward=self.exact_backward),))
+                                                                          ignore=self.ignore, exact_backward=self.exact_backward,
+                                                                          grad_out_hint=self.grad_out_hint),))
 
     def prob_flatten(self, input, target):
         """[B,C,H,W] -> [B*H*W, C] and [B,H,W] -> [B*H*W] (lovasz_loss.py:93-120)."""
@@ -442,7 +454,7 @@ class LovaszSoftmax(nn.Module):
             return loss
         loss, outs = lovasz_softmax(probas, labels, classes="present", per_image=self.per_image,
                                     ignore=self.ignore, validate_labels=self.validate_labels, return_outputs=True,
-                                    exact_backward=self.exact_backward) if probas.numel() else (lovasz_softmax(probas, labels), None)
+                                    exact_backward=self.exact_backward, grad_out_hint=self.grad_out_hint) if probas.numel() else (lovasz_softmax(probas, labels), None)
         self.last_outputs = outs
         return loss
 

@@ -63,7 +63,7 @@ def test_workspace_query_and_argument_errors(lib):
     assert lib.rtda_lovasz_workspace_bytes(1, 19, 1 << 30, 0, ctypes.byref(n)) == -2  # segment too long
     assert lib.rtda_lovasz_workspace_bytes(1, 19, 10, 0, None) == -1
     # null pointers are rejected before anything is launched
-    assert lib.rtda_lovasz_fwd(None, None, 0, 1, 19, 16, 255, 1, 0, None, 0, 1, None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.rtda_lovasz_fwd(None, None, 0, 1, 19, 16, 255, 1, 0, None, 0, 1, 1.0, None, None, None, None, None, None, None, None, None, None, None) == -1
     assert lib.rtda_lovasz_bwd_inplace(None, None, None, None, 1, 19, 16, None) == -1
     assert lib.rtda_lovasz_bwd(None, None, None, None, None, 1, 19, 16, 0, None, None) == -1
     assert lib.rtda_confusion_accumulate(None, 0, None, 0, 10, 19, 255, 1, None, None) == -1

@@ -209,6 +209,23 @@ def test_backward_twice_and_grad_out_one():
     assert np.array_equal(g3.cpu().numpy(), want["grad"] * np.float32(0.5))
 
 
+def test_grad_out_hint():
+    """The forward writes the gradient for the grad_out the caller announces (the loss weight): the backward then
+    finds nothing to do and the result is bit-exact for ANY such factor; a wrong hint is only rescaled."""
+    probas, labels = synthetic.confident_case(2, 48, 64, seed=26)
+    for per_image in (True, False):
+        for hint, go in ((0.3, 0.3), (0.5, 0.5), (0.3, 1.0)):
+            want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, per_image, grad_out=go)
+            p = probas.cuda().requires_grad_(True)
+            crit = rtda.LovaszSoftmax(ignore=255, per_image=per_image, grad_out_hint=hint, exact_backward=EXACT_BACKWARD)
+            (crit(p, labels.cuda()) * go).backward()
+            grad = p.grad.cpu().numpy()
+            if hint == go or EXACT_BACKWARD or not per_image:     # (global mode with 2 images keeps the unit gradient)
+                assert np.array_equal(grad, want["grad"]), (per_image, hint, go)
+            else:
+                assert (np.abs(grad - want["grad"]) <= 3 * np.spacing(np.abs(want["grad"]).astype(np.float32))).all()
+
+
 def test_half_precision_inputs_and_autocast():
     probas, labels = synthetic.confident_case(1, 32, 32, seed=23)
     want = c_oracle.lovasz(probas.half().float().numpy(), labels.numpy(), 255, False)

@@ -55,14 +55,14 @@ def raw_fwd_bwd(probas, labels, per_image, fill, grad_out=1.0, logits=None, fina
     if logits is None and final:
         # final-gradient mode: the forward writes every element of the NCHW gradient; the backward scales in place
         _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, int(per_image),
-                                       ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL, grad.data_ptr(), None, outs.ptr("applied"),
+                                       ws.data_ptr(), nbytes.value, _lib.GRAD_FINAL, 1.0, grad.data_ptr(), None, outs.ptr("applied"),
                                        outs.ptr("loss"), outs.ptr("class_loss"), outs.ptr("class_present"), outs.ptr("n_present"),
                                        outs.ptr("group_loss"), outs.ptr("label_errors"), outs.ptr("packed"), st), "fwd")
         _lib.check(lib.rtda_lovasz_bwd_inplace(go.data_ptr(), grad.data_ptr(), outs.ptr("applied"), ws.data_ptr(), b, c, hw, st), "bwd_inplace")
         extra = ()
     elif logits is None:
         _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, int(per_image),
-                                       ws.data_ptr(), nbytes.value, _lib.GRAD_UNIT, unit.data_ptr(), codes.data_ptr(), None, outs.ptr("loss"),
+                                       ws.data_ptr(), nbytes.value, _lib.GRAD_UNIT, 1.0, unit.data_ptr(), codes.data_ptr(), None, outs.ptr("loss"),
                                        outs.ptr("class_loss"), outs.ptr("class_present"), outs.ptr("n_present"),
                                        outs.ptr("group_loss"), outs.ptr("label_errors"), outs.ptr("packed"), st), "fwd")
         _lib.check(lib.rtda_lovasz_bwd(go.data_ptr(), unit.data_ptr(), codes.data_ptr(), outs.ptr("class_present"),
