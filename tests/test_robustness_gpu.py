@@ -331,3 +331,37 @@ def test_confusion_matrix_out_is_checked():
         with pytest.raises(ValueError, match="out must be"):
             rtda.confusion_matrix_from_logits(torch.randn(1, 19, 64, 64, device="cuda"), lab, 255, out=bad)
     assert int(good.sum()) == int((lab != 255).sum())
+
+
+def test_inplace_backward_on_an_unaligned_gradient_buffer():
+    """rtda_lovasz_bwd_inplace takes the scalar path when the gradient buffer is not 16-byte aligned (a view at an odd
+    offset of a map whose size is not a multiple of 4); the result is the aligned one."""
+    lib = _lib.load()
+    probas, labels = synthetic.confident_case(2, 33, 47, seed=81)
+    b, c, h, w = probas.shape
+    hw = h * w
+    dev = torch.device("cuda")
+    x, l = probas.to(dev).contiguous(), labels.to(dev).contiguous()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, 1, ctypes.byref(nbytes)), "ws")
+    st = torch.cuda.current_stream().cuda_stream
+    go = torch.tensor([2.0], dtype=torch.float32, device=dev)
+    got = []
+    for off in (0, 1, 3):
+        ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
+        flat = torch.full((b * c * hw + 4,), float("nan"), dtype=torch.float32, device=dev)
+        grad = flat[off:off + b * c * hw]
+        outs = lovasz_loss.LovaszOutputs(torch.zeros(lovasz_loss.LovaszOutputs.nbytes(b, c), dtype=torch.uint8, device=dev), b, c)
+        _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, 1, ws.data_ptr(), nbytes.value,
+                                       _lib.GRAD_FINAL, 1.0, grad.data_ptr(), None, outs.ptr("applied"), outs.ptr("loss"), outs.ptr("class_loss"),
+                                       outs.ptr("class_present"), outs.ptr("n_present"), outs.ptr("group_loss"), outs.ptr("label_errors"),
+                                       outs.ptr("packed"), st), "fwd")
+        _lib.check(lib.rtda_lovasz_bwd_inplace(go.data_ptr(), grad.data_ptr(), outs.ptr("applied"), ws.data_ptr(), b, c, hw, st), "bwd_inplace")
+        _lib.check(lib.rtda_lovasz_bwd_inplace(go.data_ptr(), grad.data_ptr(), outs.ptr("applied"), ws.data_ptr(), b, c, hw, st), "bwd_inplace")   # same factor again: nothing happens
+        torch.cuda.synchronize()
+        assert float(outs._view("applied")[0]) == 2.0
+        assert torch.isnan(flat[:off]).all() and torch.isnan(flat[off + b * c * hw:]).all()      # nothing written outside
+        got.append(grad.clone().view(b, c, h, w).cpu().numpy())
+    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, True, grad_out=2.0)
+    for g in got:
+        assert np.array_equal(g, want["grad"])
