@@ -700,11 +700,11 @@ def main():
         del stepper, eager, stager
         sec_steps = max(6, min(args.steps, 20))
 
-        def short(name, wl, kind, per_img, images, sc):
+        def short(name, wl, kind, per_img, images, sc, distribution="conf"):
             """value / roofline fraction of one more config, graph-replayed (eager at capture failure)."""
             try:
                 _, h2, w2, _, d2 = WORKLOADS[wl]
-                ss, sb = make_sets(wl, images, h2, w2, rank, dev, kind != "none", min_bytes=300 << 20, max_sets=4)
+                ss, sb = make_sets(wl, images, h2, w2, rank, dev, kind != "none", distribution, min_bytes=300 << 20, max_sets=4)
                 cr = criterion(kind, per_img)
                 st = Stepper(cr, ss, dev, world, use_graph=False)
                 for i in range(3):
@@ -716,7 +716,7 @@ def main():
                 px = images * h2 * w2
                 # fused CE + Lovasz from logits reads logits + labels and writes grad_logits: the same 160 B/px
                 ach = ALGO_BYTES_PER_PX * px / (per * 1e-3) / 1e9
-                secondary[name] = {"workload": f"{wl}: {d2}", "images_per_rank": images, "per_image": per_img, "loss": kind if kind != "none" else "lovasz",
+                secondary[name] = {"workload": f"{wl}: {d2}", "distribution": "D_" + distribution, "images_per_rank": images, "per_image": per_img, "loss": kind if kind != "none" else "lovasz",
                                    "value": world * px / (per * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": per, "steps": sec_steps,
                                    "scaling": sc, "launch": "cuda_graph replay" if st.graphs is not None else "eager",
                                    "roofline_frac": ach / peak, "achieved_gbs_per_gpu": ach}
@@ -729,6 +729,7 @@ def main():
         if world == 1:
             short("c1", "c1", "none", False, 1, "weak")
             short("c2_per_image", "c2", "none", True, 4, "weak")        # what each rank runs at N > 1
+            short("c2_diffuse", "c2", "none", False, 4, "weak", "diffuse")   # D_diffuse: the exact tail pruning skips most buckets
             short("c2_hybrid_fused", "c2", "fused", False, 4, "weak")
             short("c5_global", "c5", "none", False, 8, "strong")
             short("c5_hybrid_fused_global", "c5", "fused", False, 8, "strong")
