@@ -411,6 +411,13 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     }
     __syncthreads();
     if (tile == tile0) mbar_wait(&sm.mbar, 0);       // the map has arrived (block-uniform; later tiles find it there)
+#if RTDA_EXPERIMENT_PART_CUT == 3
+    { u32 x = 0;
+#pragma unroll
+      for (int j = 0; j < kPItems; ++j) x ^= key[j] ^ st[j];
+      if (x == 0x12345678u) fb_flag[seg] = 1u;
+      continue; }
+#endif
 
     if (!has_ties) {                                 // block-uniform: the common case keeps the short map
 #pragma unroll
@@ -432,6 +439,13 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         }
     }
     __syncthreads();
+#if RTDA_EXPERIMENT_PART_CUT == 2
+    { u32 x = 0;
+#pragma unroll
+      for (int j = 0; j < kPItems; ++j) x ^= key[j] ^ st[j];
+      if (x == 0x12345678u) fb_flag[seg] = 1u;
+      continue; }
+#endif
 
     // exclusive scan of the bucket counts (consecutive buckets per thread)
     const u32 per = ((u32)geo.NBK + kPThreads - 1) / kPThreads;   // <= kBMaxBuckets / kPThreads
@@ -507,7 +521,11 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             const u32 pl = (u32)v;
             const u32 d = sm_cnt[(pl >> kPB) & 0x7ffu];
             // global payload: {fg, neg, pixel index in the segment}
+#if RTDA_EXPERIMENT_PART_CUT == 1
+            if (d != kNoDst && v == 0x123456789ull) {
+#else
             if (d != kNoDst) {
+#endif
                 dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & kPosMask));
             }
         }
@@ -898,6 +916,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     local_reset(sm);
     __syncthreads();                               // the barrier is initialised, the counters are zero
     mbar_wait(&sm.mbar, 0);
+#if RTDA_EXPERIMENT_LOCAL_CUT == 4
+    if (sm.stage[tid] == 0x123456789ull) seg_bad[seg] = 1;
+    return;
+#endif
 
     u32 rk[kBItems];
     if (!local_ranks<4>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
@@ -911,6 +933,13 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             for (int j = 0; j < kBItems; ++j) rk[j] = j * kBThreads + tid;
         }
     }
+#if RTDA_EXPERIMENT_LOCAL_CUT == 3
+    { u32 x = 0;
+#pragma unroll
+      for (int j = 0; j < kBItems; ++j) x ^= rk[j];
+      if (x == 0x12345678u) seg_bad[seg] = 1;
+      return; }
+#endif
     {
         const u32 v = tid < kBTile / 32 ? (u32)__popc(sm.fg[tid].x) : 0u;
         const u32 e = block_excl_scan<kBWarps, u32>(v, sm.scan_tmp, nullptr);
@@ -934,6 +963,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             const uint2 fw = sm.fg[lr >> 5];
             const u32 f_ex = base_fg + fw.y + (u32)__popc(fw.x & ((1u << (lr & 31u)) - 1u));
             const u32 f_in = f_ex + (pay >> 31);
+#if RTDA_EXPERIMENT_LOCAL_CUT == 2
+            if (ug) ug[pay & kPayloadIdx] = __uint_as_float(f_in + r);
+            continue;
+#endif
             const float jac = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_in), __uint2float_rn(G + r + 1u - f_in)));
             const float jprev = __fsub_rn(1.0f, div_rn_counts(__uint2float_rn(G - f_ex), __uint2float_rn(G + r - f_ex)));
             const float gr = __fsub_rn(jac, jprev);
@@ -941,7 +974,11 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             eb_max = ~(u32)(e >> 32) > eb_max ? ~(u32)(e >> 32) : eb_max;
             acc.add(err, gr);
             // -sgn(fg - p) * g, times the segment's factor (err != 0 here)
+#if RTDA_EXPERIMENT_LOCAL_CUT == 1
+            if (ug && gr == 123.0f) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
+#else
             if (ug) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
+#endif
         }
     }
     flag_nonfinite(eb_max, seg_bad + seg);         // (a NaN's bit pattern compares above every finite one)
