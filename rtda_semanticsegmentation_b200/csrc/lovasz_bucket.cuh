@@ -299,9 +299,13 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
 
 // ---------------------------------------------------------------------------
 // k_part: level 1.  One block per (segment, tile of kPTile pixels), segment-major.
+constexpr u32 kPZeroBytes = 2048;                    // source of the zero fill (RTDA_SKIP_ZERO_STORES)
 struct PartShared {
     u64 exch[kPTile];
     u32 tab[kTabBins + 4];
+#if RTDA_SKIP_ZERO_STORES
+    __align__(16) u32 zeros[kPZeroBytes / 4];
+#endif
     u64 mbar;
     u32 scan_tmp[kPWarps];
     u32 skip;
@@ -336,6 +340,10 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         // every block for a full round trip to L2: 12 % of this kernel's stall samples)
         if (!sm.skip) bulk_load(sm.tab, table + (size_t)seg * kTabStride, kTabStride * (u32)sizeof(u32), &sm.mbar);
     }
+#if RTDA_SKIP_ZERO_STORES
+    for (u32 i = tid; i < kPZeroBytes / 4; i += kPThreads) sm.zeros[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the bulk stores below read these words
+#endif
     __syncthreads();
     if (sm.skip) return;
     const u32 nb_raw = nb[seg];
@@ -396,6 +404,22 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             }
         }
         for (u32 b = tid; b < NB; b += kPThreads) sm_cnt[b] = 0;
+#if RTDA_SKIP_ZERO_STORES
+        // The gradient of the whole tile is first written as the zero most of it is (two thirds of lovasz_grad's
+        // first differences round to exactly 0 in fp32 at c2), so that level 2 scatters only the non-zero third:
+        // its 4-byte stores, one LSU cycle per lane, are what bounds its last phase.  The fill is a handful of bulk
+        // copies (TMA, shared -> global) from a block of zeros, issued by one thread: no LSU work at all.  Segments
+        // whose length is not a multiple of 4 elements (16-byte granularity of the copies) store element-wise below.
+        const bool bulk_zero = unit_grad != nullptr && (n & 3u) == 0u;
+        if (bulk_zero && tid == 0) {
+            char *zdst = reinterpret_cast<char *>(unit_grad + (size_t)seg * n + tile_base);
+            for (u32 off = 0; off < count * 4u; off += kPZeroBytes) {
+                const u32 bytes = count * 4u - off < kPZeroBytes ? count * 4u - off : kPZeroBytes;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(zdst + off), "r"(smem_u32(sm.zeros)), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < kPItems; ++j) {
             const bool fg = code[j] == c;
@@ -404,8 +428,12 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             st[j] = (fg ? kPayloadFg : 0u) | neg;
             if (code[j] != 255u) {
                 if (key[j] != 0xFFFFFFFFu) st[j] |= kLive;
+#if RTDA_SKIP_ZERO_STORES
+                if (unit_grad && !bulk_zero) unit_grad[(size_t)seg * n + i0 + 32 * j] = 0.0f;
+#else
                 else if (unit_grad)       // error exactly 0: gradient 0, not sorted (rare: the address is worked out here)
                     unit_grad[(size_t)seg * n + i0 + 32 * j] = 0.0f;
+#endif
             }
         }
     }
@@ -531,6 +559,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         }
     }
     }
+#if RTDA_SKIP_ZERO_STORES
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // the zero fills are complete before the block ends
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -880,6 +911,9 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     const float gscale = seg_scale[seg];             // 1, or the (1 / G) / K of the final gradient (k_split)
     if (!(pa.w & kPlanLive)) return;
     const u32 cnt = pa.x;
+#if RTDA_SKIP_ZERO_STORES
+    if (pa.w & kPlanTail) return;                    // all zeros, already written by k_part
+#endif
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
         // one bulk copy brings the bucket in (16-byte granularity: an odd count reads one slot of padding)
@@ -892,7 +926,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         const size_t pb = (size_t)blockIdx.x + RTDA_LOCAL_PREFETCH;
         if (pb < (size_t)gridDim.x) {
             const uint4 fa = plan[2 * pb];
-            if (fa.w & kPlanLive)
+            if ((fa.w & kPlanLive) && !(RTDA_SKIP_ZERO_STORES && (fa.w & kPlanTail)))
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(regions + pb * (size_t)kBTile), "r"(((fa.x + 1u) & ~1u) * 8u) : "memory");
         }
     }
@@ -905,12 +939,14 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     const LinMap lm = {pl.x, (pa.w & kPlanLin) ? pl.y : 0xFFFFFFFFu, pl.z, pl.w};
     if (pa.w & kPlanTail) {
         // only background elements behind the last foreground element (k_plan): gradient exactly 0, err * 0 to the loss
+#if !RTDA_SKIP_ZERO_STORES                         // (else k_part has written these zeros, and the bucket is not even staged)
         __syncthreads();                           // the barrier is initialised
         mbar_wait(&sm.mbar, 0);
         if (unit_grad) {
             float *ug0 = unit_grad + (size_t)seg * (size_t)geo.n;
             for (u32 i = tid; i < cnt; i += kBThreads) ug0[(u32)sm.stage[i] & kPayloadIdx] = 0.0f;
         }
+#endif
         return;
     }
     local_reset(sm);
@@ -976,6 +1012,8 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
             // -sgn(fg - p) * g, times the segment's factor (err != 0 here)
 #if RTDA_EXPERIMENT_LOCAL_CUT == 1
             if (ug && gr == 123.0f) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
+#elif RTDA_SKIP_ZERO_STORES
+            if (ug && gr != 0.0f) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
 #else
             if (ug) ug[pay & kPayloadIdx] = __fmul_rn((pay & kPayloadNeg) ? gr : -gr, gscale);
 #endif
