@@ -182,19 +182,32 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         // kSplitUnroll runs per warp and iteration: their loads are issued before any of them is
         // binned, so a warp keeps that many DRAM round trips in flight instead of one
         const u32 ustep = gridDim.y * wpb;
+        // (the index arithmetic was 42 % of this kernel's instructions as two integer divisions per sample:
+        // the run's place inside its stride by a mask when SG is a power of two - it is 16 for every segment of
+        // 256 K elements or more -, the image of a pixel by a multiplication with 1 / HW and one correction step)
+        const u32 sg_mask = (SG & (SG - 1u)) == 0u ? SG - 1u : 0xFFFFFFFFu;
+        const float rcp_hw = 1.0f / (float)HW;
+        const float *pc = probas + ((size_t)g * geo.Bg * geo.C + c) * (size_t)HW;   // class c of the group's first image
+        const size_t img_step = (size_t)(geo.C - 1) * HW;                          // i + bi * img_step: same class, image bi
         for (u32 u0 = blockIdx.y * wpb + (tid >> 5); u0 < runs; u0 += kSplitUnroll * ustep) {
             u32 code[kSplitUnroll];
             float p[kSplitUnroll];
 #pragma unroll
             for (int q = 0; q < kSplitUnroll; ++q) {
                 const u32 u = u0 + (u32)q * ustep;
-                const u32 i = 32u * SG * u + 32u * ((u * 7u) % SG) + lane;
+                const u32 u7 = u * 7u;
+                const u32 i = 32u * SG * u + 32u * (sg_mask != 0xFFFFFFFFu ? (u7 & sg_mask) : (u7 % SG)) + lane;
                 code[q] = 255u;
                 p[q] = 0.0f;
                 if (u < runs && i < n) {
-                    const u32 bi = i / HW, hw = i - bi * HW;
+                    u32 bi = 0;
+                    if (geo.Bg > 1) {
+                        bi = (u32)(__uint2float_rz(i) * rcp_hw);      // within 1 of i / HW (i < 2^30)
+                        if (bi * HW > i) --bi;
+                        if ((bi + 1u) * HW <= i) ++bi;
+                    }
                     code[q] = cg[i];                 // two independent loads
-                    p[q] = probas[(((size_t)g * geo.Bg + bi) * geo.C + c) * (size_t)HW + hw];
+                    p[q] = pc[(size_t)i + bi * img_step];
                 }
             }
 #pragma unroll
@@ -419,6 +432,11 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (unit_grad != nullptr && !bulk_zero) {    // (block-uniform, rare; ignored pixels included, as in the bulk fill)
+            float *ugz = unit_grad + (size_t)seg * n + i0;
+            for (u32 j = 0; j < (u32)kPItems; ++j)
+                if (idx0 + 32u * j < count) ugz[32u * j] = 0.0f;
+        }
 #endif
 #pragma unroll
         for (int j = 0; j < kPItems; ++j) {
@@ -429,7 +447,6 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             if (code[j] != 255u) {
                 if (key[j] != 0xFFFFFFFFu) st[j] |= kLive;
 #if RTDA_SKIP_ZERO_STORES
-                if (unit_grad && !bulk_zero) unit_grad[(size_t)seg * n + i0 + 32 * j] = 0.0f;
 #else
                 else if (unit_grad)       // error exactly 0: gradient 0, not sorted (rare: the address is worked out here)
                     unit_grad[(size_t)seg * n + i0 + 32 * j] = 0.0f;
