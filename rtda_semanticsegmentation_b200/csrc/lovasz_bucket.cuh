@@ -140,8 +140,9 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
         if (tid == 0 && blockIdx.y == 0) nb_out[seg] = 0;
         if (geo.final_grad && grad) {
             // the final gradient has no separate zero-filling pass: the planes of an absent class are zeroed here
-            float *gb = grad + (size_t)seg * (size_t)geo.n;      // one image per group: [B][C][HW] is [G][C][n]
-            for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.n; i += gridDim.y * kSplitThreads) gb[i] = 0.0f;
+            float *gb = grad + geo.grad_seg_off(seg);            // class c of the group's (first) image
+            for (u32 bi = 0; bi < (u32)geo.Bg; ++bi, gb += (size_t)geo.C * (size_t)geo.HW)
+                for (u32 i = blockIdx.y * kSplitThreads + tid; i < (u32)geo.HW; i += gridDim.y * kSplitThreads) gb[i] = 0.0f;
         }
         return;
     }
@@ -322,6 +323,8 @@ struct PartShared {
     u64 mbar;
     u32 scan_tmp[kPWarps];
     u32 skip;
+    u32 tile_add;
+    float *zbase;        // where the segment's gradient starts (Geom.grad_seg_off)
     u32 arrays[1];       // cnt[nbk_pad] (count | fg << 16, then the global destination), pre[nbk_pad]
 };
 constexpr u32 kNoDst = 0xFFFFFFFFu;
@@ -347,6 +350,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     // other blocks of this kernel may raise the flag while this one starts: one thread decides for the block
     if (tid == 0) {
         sm.skip = (seg_fg[seg] == 0 || ld_relaxed(fb_flag + seg) != 0) ? 1u : 0u;
+        sm.zbase = unit_grad ? unit_grad + geo.grad_seg_off(seg) : nullptr;
         mbar_init(&sm.mbar, 1);
         // the segment's map (16 KB) comes in by one bulk copy; it is first needed after the tile's own
         // loads have returned, so its latency is hidden behind them (a register-staged copy stalled
@@ -423,9 +427,13 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         // its 4-byte stores, one LSU cycle per lane, are what bounds its last phase.  The fill is a handful of bulk
         // copies (TMA, shared -> global) from a block of zeros, issued by one thread: no LSU work at all.  Segments
         // whose length is not a multiple of 4 elements (16-byte granularity of the copies) store element-wise below.
+        // (several images per group in final-gradient mode, Geom.img_step: a tile inside one image is contiguous in NCHW too)
+        // (Geom.img_step != 0: HW is a multiple of the tile, so a tile lies in one image and is contiguous in NCHW too)
         const bool bulk_zero = unit_grad != nullptr && (n & 3u) == 0u;
+        // the pixel index of the tile's first element; read after the barriers below, in the read-out
+        if (tid == 0) sm.tile_add = tile_base + (tile_base - hw_tile) / HW * (u32)geo.img_step;
         if (bulk_zero && tid == 0) {
-            char *zdst = reinterpret_cast<char *>(unit_grad + (size_t)seg * n + tile_base);
+            char *zdst = reinterpret_cast<char *>(sm.zbase + sm.tile_add);
             for (u32 off = 0; off < count * 4u; off += kPZeroBytes) {
                 const u32 bytes = count * 4u - off < kPZeroBytes ? count * 4u - off : kPZeroBytes;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(zdst + off), "r"(smem_u32(sm.zeros)), "r"(bytes) : "memory");
@@ -433,9 +441,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (unit_grad != nullptr && !bulk_zero) {    // (block-uniform, rare; ignored pixels included, as in the bulk fill)
-            float *ugz = unit_grad + (size_t)seg * n + i0;
+            float *ugz = sm.zbase;
             for (u32 j = 0; j < (u32)kPItems; ++j)
-                if (idx0 + 32u * j < count) ugz[32u * j] = 0.0f;
+                if (idx0 + 32u * j < count) ugz[i0 + 32u * j] = 0.0f;     // (img_step == 0 here)
         }
 #endif
 #pragma unroll
@@ -558,6 +566,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
     __syncthreads();
 
     u64 *dst = out + (size_t)seg * geo.NBK * (size_t)kBTile;
+    const u32 t_add = sm.tile_add;                   // the pixel index of the tile's first element
 #pragma unroll
     for (int k = 0; k < kPItems; ++k) {
         const u32 pos = k * kPThreads + tid;
@@ -571,7 +580,7 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
 #else
             if (d != kNoDst) {
 #endif
-                dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (tile_base + (pl & kPosMask));
+                dst[d + pos] = (v & 0xFFFFFFFFC0000000ull) | (t_add + (pl & kPosMask));
             }
         }
     }
@@ -626,7 +635,8 @@ __device__ __forceinline__ u32 field_sum(u32 w) {   // sum of the W-bit fields o
 struct LinMap { u32 lo, R, sh, M; };             // in-bucket linear map (k_plan); R = 0xFFFFFFFF: use the segment's map
 template <int W>
 __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restrict__ tab, const u32 *__restrict__ tie,
-                                            bool has_ties, const LinMap lm, u32 n, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
+                                            bool has_ties, const LinMap lm, const Geom &geo, u32 cnt, u32 xmax, u32 (&rk)[kBItems]) {
+    const u32 n = (u32)geo.n;
     const u32 lin_lo = lm.lo, lin_R = lm.R, lin_sh = lm.sh, lin_M = lm.M;
     const bool lin = lin_R != 0xFFFFFFFFu;           // block-uniform
     constexpr u32 FW = 32 / W;                       // fields per word
@@ -653,7 +663,7 @@ __device__ __forceinline__ bool local_ranks(LocalShared &sm, const u32 *__restri
                 d = d < lin_R ? d : lin_R;
                 x16 = __umulhi(d << lin_sh, lin_M);
             } else {
-                x16 = cdf_pos(has_ties, (u32)(e >> 32), (u32)e & kPayloadIdx, n, tab, tie, xmax) & 0xffffu;
+                x16 = cdf_pos(has_ties, (u32)(e >> 32), geo.seg_index((u32)e & kPayloadIdx), n, tab, tie, xmax) & 0xffffu;
             }
             const u32 f = x16 >> FSHIFT;
             const u32 sh = (f % FW) * W;
@@ -960,7 +970,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
         __syncthreads();                           // the barrier is initialised
         mbar_wait(&sm.mbar, 0);
         if (unit_grad) {
-            float *ug0 = unit_grad + (size_t)seg * (size_t)geo.n;
+            float *ug0 = unit_grad + geo.grad_seg_off(seg);
             for (u32 i = tid; i < cnt; i += kBThreads) ug0[(u32)sm.stage[i] & kPayloadIdx] = 0.0f;
         }
 #endif
@@ -975,10 +985,10 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
 #endif
 
     u32 rk[kBItems];
-    if (!local_ranks<4>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+    if (!local_ranks<4>(sm, tab, tie, has_ties, lm, geo, cnt, xmax, rk)) {
         local_reset(sm);
         __syncthreads();
-        if (!local_ranks<8>(sm, tab, tie, has_ties, lm, (u32)geo.n, cnt, xmax, rk)) {
+        if (!local_ranks<8>(sm, tab, tie, has_ties, lm, geo, cnt, xmax, rk)) {
             // 256 or more elements in one fine slot (exact ties of saturated probabilities): order the
             // whole bucket by (key, pixel index) with a bitonic network in place; rank = position
             local_sort_all(sm, cnt);
@@ -1001,7 +1011,7 @@ k_local(const u64 *__restrict__ regions, Geom geo, const u32 *__restrict__ seg_f
     __syncthreads();
 
     // phase D: ranks -> lovasz_grad, dot product, gradient (lovasz_loss.py:60-69,180), as in k_rank_last
-    float *ug = unit_grad ? unit_grad + (size_t)seg * (size_t)geo.n : nullptr;
+    float *ug = unit_grad ? unit_grad + geo.grad_seg_off(seg) : nullptr;
     LossAcc acc = {0, 0};
     u32 eb_max = 0;
 #pragma unroll
