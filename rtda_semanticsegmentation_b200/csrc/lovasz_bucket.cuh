@@ -291,25 +291,7 @@ k_split(const float *__restrict__ probas, const unsigned char *__restrict__ code
     if (tid == 0) { tab[kTabBins] = (u32)scale; nb_out[seg] = NB | (seg_ties ? kNbTies : 0u); }
 }
 
-// mbarrier + bulk asynchronous copy (cp.async.bulk, the 1-D TMA path): one thread starts the copy,
-// the data arrives in shared memory without passing through registers, every reader waits on the barrier.
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    u32 ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
+// (mbarrier + bulk-copy helpers: common.cuh)
 
 // ---------------------------------------------------------------------------
 // k_part: level 1.  One block per (segment, tile of kPTile pixels), segment-major.
