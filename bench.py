@@ -771,13 +771,16 @@ def main():
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     # per-kernel compulsory traffic of each stage's own job (bytes per launch), for the kernel table
     E = C * px_step
+    # plain Lovasz: the forward writes the finished gradient where the shape allows it (always per image; global batches
+    # with HW % 4096 == 0), the backward is then an in-place rescale that exits at once for grad_out = 1
+    final_mode = args.hybrid == "none" and bool(_lib.load().rtda_lovasz_final_grad_supported(imgs, C, H * W, int(per_image)))
     own_bytes = {
         "memset_workspace": None,
         "k_prep": px_step * (8 + 1) if args.hybrid != "fused" else E * 8 + px_step * 9,   # labels in, class codes out (+ logits in, probabilities out)
         "k_split": E // 16 * 8,                            # 1/16 sample, half of every 32-byte sector used
-        "k_part": E * 4 + E * 1 + E * 8,                   # probabilities + codes (re-read per class) in, pairs out
+        "k_part": E * 4 + E * 1 + E * 8 + E * 4,           # probabilities + codes (re-read per class) in, pairs out, the gradient's zero fill out
         "k_plan": None,
-        "k_local": E * 8 + E * 4,                          # pairs in, 4-byte gradient scatter out
+        "k_local": E * 8 + E * 4 // 3,                     # pairs in, the non-zero third of the gradient scattered out
         "k_hist_fb": None,
         "k_scan": None,
         "k_sort_pass<0,probas>": E * 4 + px_step * 1 + E * 8,
@@ -785,7 +788,7 @@ def main():
         "k_sort_pass<2>": E * 16,
         "k_rank_last": E * 8 + E * 4,
         "k_finalize": None,
-        "k_bwd": E * 8 if args.hybrid != "fused" else E * 12 + px_step,
+        "k_bwd": (None if final_mode else E * 8) if args.hybrid != "fused" else E * 12 + px_step,
     }
     if fb_segments == 0:
         # no segment fell back: the LSD kernels were launched and exited at once, they moved no data
@@ -807,9 +810,11 @@ def main():
     kernels.sort(key=lambda k: -k["share_of_step"])
     dom = kernels[0]
     gaps = stages.get("gaps_between_launches", (0.0, 0))
-    # DRAM floor of the two-movement design: probabilities 4 + codes 1 in, pairs 8 out (k_part); pairs 8 in,
-    # gradient 4 out (k_local); unit gradient 4 in, gradient 4 out (k_bwd) = 33 B per element, + labels
-    floor_bytes = 33.0 * E + 9.0 * px_step
+    # DRAM floor of the two-movement design: probabilities 4 + codes 1 in, pairs 8 out, gradient zeros 4 out (k_part);
+    # pairs 8 in (k_local; its scatter of the non-zero gradients lands on lines the fill wrote) = 25 B per element;
+    # with the unit gradient (fused CE + Lovasz, exact_backward) the backward pass reads 4 and writes 4 more = 33; + labels
+    floor_per_elem = 25.0 if final_mode else 33.0
+    floor_bytes = floor_per_elem * E + 9.0 * px_step
     floor_ms = floor_bytes / (peak * 1e9) * 1e3
 
     line = {
@@ -841,7 +846,7 @@ def main():
             "peak_source": peak_src,
             "what": "whole fwd+bwd step: 160 B/px algorithmic bytes x pixels / CUDA-event step time (the exact sort of 19 x N keys moves ~0.6 KB/px, so the algorithmic fraction is far below each kernel's own DRAM fraction)",
             "design_floor_ms": floor_ms, "fraction_of_floor": floor_ms / ms_step,
-            "design_floor_what": "DRAM floor of the two-movement design: 33 B per (pixel, class) element + 9 B per pixel at the measured peak",
+            "design_floor_what": f"DRAM floor of the two-movement design: {floor_per_elem:.0f} B per (pixel, class) element + 9 B per pixel at the measured peak",
             "dominant_kernel": dom["name"], "dominant_share_of_step": dom["share_of_step"],
             "dominant_own_gbs": dom["own_gbs"], "dominant_own_frac_of_peak": dom["own_frac_of_peak"],
             "kernels": kernels,

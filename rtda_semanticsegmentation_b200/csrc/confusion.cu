@@ -401,7 +401,10 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
         const size_t ssm = (size_t)n_class * n_class * sizeof(u32);
 #if RTDA_CM_TMA
         // staged by bulk copies: 16-byte aligned maps (torch allocations are; a slice starting at an odd element is not)
-        if (n_class <= kCtMaxClasses && ((uintptr_t)labels & 15) == 0 && ((uintptr_t)preds & 15) == 0 && n >= kCtChunk) {
+        // ... and several chunks per SM: on one 1024 x 2048 map (3.5 chunks per SM, 20 of the 148 blocks idle) it is no
+        // faster than k_confusion_stream (10.2-10.8 against 10.5 us), from 8 chunks per SM on it wins (8 maps: 42.5 against 47.7 us)
+        if (n_class <= kCtMaxClasses && ((uintptr_t)labels & 15) == 0 && ((uintptr_t)preds & 15) == 0 &&
+            n >= (long long)kCtChunk * 8 * sm_count()) {
             const size_t tsm = confusion_tma_smem<LabelT, PredT>(n_class);
             static bool attr_done[64] = {false};
             int dev = 0;

@@ -82,3 +82,20 @@ def test_full_size_validation_map_and_checksum():
     assert np.array_equal(h, c_oracle.confusion(lab.cpu().numpy(), prd.cpu().numpy(), 19, 255))
     assert h.sum() == int((lab != 255).sum())
     assert np.array_equal(h.sum(1), np.bincount(lab[lab != 255].cpu().numpy(), minlength=19))
+
+
+@pytest.mark.parametrize("tail", [0, 1, 15, 16, 2049])
+def test_bulk_copy_staged_kernel_on_a_batched_call(tail):
+    """Calls of 8 chunks per SM or more take k_confusion_tma (maps staged in shared memory by bulk copies).  Three
+    1024x2048 maps plus a ragged tail: the last chunk is partial, its end not a multiple of the 16 pixels a copy moves."""
+    lab, prd = synthetic.validation_maps(3, 1024, 2048, seed=77, device="cuda")
+    n = 3 * 1024 * 2048 - 4096 + tail
+    lab, prd = lab.reshape(-1)[:n].contiguous(), prd.reshape(-1)[:n].contiguous()
+    prd[5] = 19; prd[6] = -1; lab[7] = 300; lab[8] = -7            # out-of-range values count nothing (utils.py:78-83)
+    want = c_oracle.confusion(lab.cpu().numpy(), prd.cpu().numpy(), 19, 255)
+    assert np.array_equal(rtda.confusion_matrix(lab, prd, 19, 255).cpu().numpy(), want)
+    # narrower storage types of either map (9 and 5 bytes per pixel)
+    lab8 = torch.where((lab >= 0) & (lab < 256), lab, torch.full_like(lab, 255)).to(torch.uint8)
+    want8 = c_oracle.confusion(lab8.cpu().numpy().astype(np.int64), prd.cpu().numpy(), 19, 255)
+    assert np.array_equal(rtda.confusion_matrix(lab8, prd, 19, 255).cpu().numpy(), want8)
+    assert np.array_equal(rtda.confusion_matrix(lab8, prd.to(torch.int32), 19, 255).cpu().numpy(), want8)
