@@ -95,8 +95,8 @@ int rtda_lovasz_set_sort_path(int path);
  *                    rtda_lovasz_bwd_inplace: nothing to do for grad_out = h, one in-place multiplication
  *                    otherwise.  `applied_scale` [1] fp32 records which grad_out the buffer currently holds.
  *   RTDA_GRAD_UNIT   `grad` [G][C][n] fp32, n = B*HW/G, receives the unit gradient -g_rank * sgn(fg - p)
- *                    before the 1/K and 1/G factors; rows of absent classes and ignored pixels are NOT
- *                    written.  The backward is rtda_lovasz_bwd (bit-exact for ANY grad_out) or, fused with the
+ *                    before the 1/K and 1/G factors; rows of absent classes and ignored pixels are not
+ *                    defined (they may or may not be written: the backward never reads them).  The backward is rtda_lovasz_bwd (bit-exact for ANY grad_out) or, fused with the
  *                    softmax and cross-entropy backward, rtda_hybrid_bwd; both read `codes` as well.
  * Forward outputs:
  *   grad          see above; may be NULL (loss only, e.g. under torch.no_grad()).
@@ -121,10 +121,10 @@ int rtda_lovasz_set_sort_path(int path);
  */
 #define RTDA_GRAD_UNIT 0
 #define RTDA_GRAD_FINAL 1
-/* 1 when RTDA_GRAD_FINAL is available for this shape: one image per group (per_image, or B = 1), where the
- * NCHW layout [B][C][HW] is the segment layout [G][C][n].  With several images per group rtda_lovasz_fwd
- * returns RTDA_E_RANGE for it (scattering into B planes per class measured slower than the contiguous unit
- * gradient + rtda_lovasz_bwd): use RTDA_GRAD_UNIT there. */
+/* 1 when RTDA_GRAD_FINAL is available for this shape: always with one image per group (per_image, or B = 1),
+ * where the NCHW layout [B][C][HW] is the segment layout [G][C][n]; with several images per group (global mode,
+ * B > 1) when HW is a multiple of 4096 and C * B * HW < 2^30 (the sorted pairs then carry the element's NCHW
+ * offset).  Otherwise rtda_lovasz_fwd returns RTDA_E_RANGE for it: use RTDA_GRAD_UNIT there. */
 int rtda_lovasz_final_grad_supported(int64_t B, int C, int64_t HW, int per_image);
 int rtda_lovasz_fwd(const float *probas, const void *labels, int label_kind,
                     int64_t B, int C, int64_t HW, int64_t ignore, int has_ignore, int per_image,

@@ -200,7 +200,7 @@ def _forward_native(probas: torch.Tensor, labels: torch.Tensor, ignore, per_imag
     _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, int(per_image), _lib.ctypes.byref(nbytes)),
                "rtda_lovasz_workspace_bytes")
     ws = _workspace(dev, stream, nbytes.value)
-    # final-gradient mode where the shape allows it (always with one image per group), else the unit gradient
+    # final-gradient mode where the shape allows it (per image always; global batches of maps with H*W % 4096 == 0), else the unit gradient
     final = need_grad and not exact_backward and bool(lib.rtda_lovasz_final_grad_supported(b, c, hw, int(per_image)))
     grad = torch.empty((b, c, h, w) if final else (b * c * hw,), dtype=torch.float32, device=dev) if need_grad else None
     codes = torch.empty(b * hw, dtype=torch.uint8, device=dev) if need_grad and not final else None
