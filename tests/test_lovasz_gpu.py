@@ -455,3 +455,29 @@ def test_saturated_predictions_stay_on_the_bucket_path(sort_path, boost, scale):
     assert_matches_oracle(probas.numpy(), labels.numpy(), 255, False, tag=f"boost {boost}")
     if sort_path == "bucket":
         assert int(rtda.segment_sort_paths((2, 19, 512, 512), False).sum()) == 0
+
+
+def test_global_batch_written_in_nchw_with_mixed_sort_paths(sort_path):
+    """Global mode over several images (one sort problem per class, B planes 19*HW apart in the caller's gradient),
+    maps of a multiple of 4096 pixels so that the forward writes the finished NCHW gradient: ignored pixels in every
+    image, a class absent from the batch, a class present in one image only, a class of constant probability (one
+    massive tie: its segment overflows a bucket region and is redone by the LSD kernels while the others stay on the
+    bucket path), a class with exactly-zero errors.  Bit for bit against the C oracle, for grad_out 1 and 0.5."""
+    rng = np.random.default_rng(5)
+    b, c, h, w = 3, 7, 64, 192
+    labels = rng.integers(0, 5, size=(b, h, w))
+    labels[0, :8] = 255
+    labels[1, :, :16] = 255
+    labels[2][rng.random((h, w)) < 0.1] = 255
+    labels[labels == 4] = 0
+    labels[1, 40:, 100:] = 4                          # class 4 in image 1 only; classes 5 and 6 absent
+    logits = rng.normal(size=(b, c, h, w)) * 2.0
+    logits[np.arange(b)[:, None, None], np.clip(labels, 0, c - 1), np.arange(h)[None, :, None], np.arange(w)[None, None, :]] += 3.0
+    probas = torch.softmax(torch.from_numpy(logits), 1).float().numpy()
+    probas[:, 2] = np.float32(0.3)                    # constant: every background error equal, every foreground error equal
+    probas[:, 3][labels == 3] = 1.0                   # foreground errors exactly 0: never sorted
+    assert_matches_oracle(probas, labels, tag="nchw global")
+    assert_matches_oracle(probas, labels, grad_out=0.5, tag="nchw global, grad_out 0.5")
+    if sort_path == "bucket":
+        fb = rtda.segment_sort_paths((b, c, h, w), False).cpu().numpy().ravel()
+        assert fb[2] == 1 and fb[0] == 0, fb
