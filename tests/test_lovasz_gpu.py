@@ -481,3 +481,23 @@ def test_global_batch_written_in_nchw_with_mixed_sort_paths(sort_path):
     if sort_path == "bucket":
         fb = rtda.segment_sort_paths((b, c, h, w), False).cpu().numpy().ravel()
         assert fb[2] == 1 and fb[0] == 0, fb
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_global_batches_of_4096_multiples_random(seed):
+    """Randomised global batches whose maps are multiples of 4096 pixels (the shapes whose finished gradient the forward
+    writes in NCHW): batch, class count, sharpness, ignore share and saturation drawn per case; bit for bit against the
+    C oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    b, c = int(rng.integers(2, 6)), int(rng.integers(2, 9))
+    h, w = 64, 64 * int(rng.integers(1, 4))
+    labels = rng.integers(0, c, size=(b, h, w))
+    labels[rng.random((b, h, w)) < rng.choice([0.0, 0.05, 0.5])] = 255
+    if seed % 3 == 0:
+        labels[labels == c - 1] = 0                    # one class absent
+    sharp = float(rng.choice([0.5, 3.0, 12.0, 30.0]))  # 30: saturated softmax, thousands of exact ties and exact zeros
+    logits = rng.normal(size=(b, c, h, w)) * 2.0
+    onehot = np.clip(labels, 0, c - 1)
+    logits[np.arange(b)[:, None, None], onehot, np.arange(h)[None, :, None], np.arange(w)[None, None, :]] += sharp
+    probas = torch.softmax(torch.from_numpy(logits).float(), 1).numpy()
+    assert_matches_oracle(probas, labels, tag=f"b{b} c{c} {h}x{w} sharp {sharp}")
