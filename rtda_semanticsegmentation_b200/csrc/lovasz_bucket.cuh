@@ -411,7 +411,9 @@ k_part(const float *__restrict__ probas, const unsigned char *__restrict__ codes
         // whose length is not a multiple of 4 elements (16-byte granularity of the copies) store element-wise below.
         // (several images per group in final-gradient mode, Geom.img_step: a tile inside one image is contiguous in NCHW too)
         // (Geom.img_step != 0: HW is a multiple of the tile, so a tile lies in one image and is contiguous in NCHW too)
-        const bool bulk_zero = unit_grad != nullptr && (n & 3u) == 0u;
+        // (the copies need 16-byte aligned addresses: a segment length that is a multiple of 4 with HW % 4 != 0 - four
+        // 33 x 33 maps - comes with a buffer that is only promised to be 4-byte aligned)
+        const bool bulk_zero = unit_grad != nullptr && (n & 3u) == 0u && (reinterpret_cast<size_t>(unit_grad) & 15) == 0;
         // the pixel index of the tile's first element; read after the barriers below, in the read-out
         if (tid == 0) sm.tile_add = tile_base + (tile_base - hw_tile) / HW * (u32)geo.img_step;
         if (bulk_zero && tid == 0) {

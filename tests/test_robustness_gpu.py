@@ -365,3 +365,39 @@ def test_inplace_backward_on_an_unaligned_gradient_buffer():
     want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, True, grad_out=2.0)
     for g in got:
         assert np.array_equal(g, want["grad"])
+
+
+def test_unit_gradient_buffer_at_an_odd_offset_with_a_segment_of_a_multiple_of_4():
+    """Global mode over four 33x33 maps: the segment length (4356) is a multiple of 4 although HW is not, so the C ABI
+    only asks for a 4-byte aligned unit-gradient buffer - k_part's zero fill must then go element by element, not by
+    16-byte bulk copies.  The result equals the aligned one and nothing is written outside the buffer."""
+    lib = _lib.load()
+    probas, labels = synthetic.confident_case(4, 33, 33, seed=83)
+    b, c, h, w = probas.shape
+    hw = h * w
+    dev = torch.device("cuda")
+    x, l = probas.to(dev).contiguous(), labels.to(dev).contiguous()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.rtda_lovasz_workspace_bytes(b, c, hw, 0, ctypes.byref(nbytes)), "ws")
+    st = torch.cuda.current_stream().cuda_stream
+    go = torch.tensor([1.0], dtype=torch.float32, device=dev)
+    got = []
+    for off in (0, 1, 2):
+        ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
+        flat = torch.full((b * c * hw + 4,), float("nan"), dtype=torch.float32, device=dev)
+        unit = flat[off:off + b * c * hw]
+        codes = torch.empty(b * hw, dtype=torch.uint8, device=dev)
+        outs = lovasz_loss.LovaszOutputs(torch.zeros(lovasz_loss.LovaszOutputs.nbytes(1, c), dtype=torch.uint8, device=dev), 1, c)
+        _lib.check(lib.rtda_lovasz_fwd(x.data_ptr(), l.data_ptr(), _lib.label_kind(l.dtype), b, c, hw, 255, 1, 0, ws.data_ptr(), nbytes.value,
+                                       _lib.GRAD_UNIT, 1.0, unit.data_ptr(), codes.data_ptr(), None, outs.ptr("loss"), outs.ptr("class_loss"),
+                                       outs.ptr("class_present"), outs.ptr("n_present"), outs.ptr("group_loss"), outs.ptr("label_errors"),
+                                       outs.ptr("packed"), st), "fwd")
+        grad = torch.empty(b, c, h, w, dtype=torch.float32, device=dev)
+        _lib.check(lib.rtda_lovasz_bwd(go.data_ptr(), unit.data_ptr(), codes.data_ptr(), outs.ptr("class_present"), outs.ptr("n_present"),
+                                       b, c, hw, 0, grad.data_ptr(), st), "bwd")
+        torch.cuda.synchronize()
+        assert torch.isnan(flat[:off]).all() and torch.isnan(flat[off + b * c * hw:]).all()      # nothing written outside
+        got.append(grad.cpu().numpy())
+    want = c_oracle.lovasz(probas.numpy(), labels.numpy(), 255, False)
+    for g in got:
+        assert np.array_equal(g, want["grad"])
