@@ -204,17 +204,9 @@ k_confusion_stream(const LabelT *__restrict__ labels, const PredT *__restrict__ 
 #ifndef RTDA_CM_TMA            // 0 = k_confusion_stream only
 #define RTDA_CM_TMA 1
 #endif
-#ifndef RTDA_CT_THREADS
-#define RTDA_CT_THREADS 1024
-#endif
-#ifndef RTDA_CT_CHUNK
-#define RTDA_CT_CHUNK 4096
-#endif
-constexpr int kCtThreads = RTDA_CT_THREADS;
-constexpr int kCtChunk = RTDA_CT_CHUNK;         // pixels per stage
-constexpr int kCtStages = 6 * 2048 / kCtChunk;  // 192 KB of int64 maps in flight per SM
-constexpr int kCtMaxClasses = 77;               // 6 x 32 KB of stages + 77^2 bins fit the 227 KB of an SM
-constexpr int kCtPer = kCtChunk / kCtThreads;   // pixels per thread and chunk (4: two pairs kCtChunk / 2 apart)
+// The ring is a template parameter set (THREADS, CHUNK pixels per stage, STAGES); <1024, 4096, 3> is what runs: few, large
+// copies and one block-wide barrier per 4096 pixels (<512, 2048, 6> and <1024, 2048, 6>: 52.9 / 50.8 us for 8 maps against 42.5).
+constexpr int kCtMaxClasses = 77;               // 192 KB of stages + 77^2 bins fit the 227 KB of an SM
 
 template <typename T>
 __device__ __forceinline__ void ct_pair(const T *base, u32 i, long long *o) { o[0] = (long long)base[i]; o[1] = (long long)base[i + 1]; }
@@ -227,11 +219,13 @@ __device__ __forceinline__ void ct_pair<int>(const int *base, u32 i, long long *
     const int2 v = *reinterpret_cast<const int2 *>(base + i); o[0] = v.x; o[1] = v.y;
 }
 
-template <typename LabelT, typename PredT>
+template <typename LabelT, typename PredT, int kCtThreads, int kCtChunk, int kCtStages>
 __global__ void __launch_bounds__(kCtThreads, 1)
 k_confusion_tma(const LabelT *__restrict__ labels, const PredT *__restrict__ preds, long long n, int n_class,
                 long long ignore, int has_ignore, unsigned long long *__restrict__ hist) {
     extern __shared__ __align__(128) unsigned char ct_smem[];
+    constexpr int kCtPer = kCtChunk / kCtThreads;   // pixels per thread and chunk (4: two pairs kCtChunk / 2 apart)
+    static_assert(kCtPer == 4, "a thread takes two pairs of pixels per chunk");
     constexpr u32 kStageBytes = kCtChunk * (sizeof(LabelT) + sizeof(PredT));
     u64 *full = reinterpret_cast<u64 *>(ct_smem + (size_t)kCtStages * kStageBytes);
     u32 *sh = reinterpret_cast<u32 *>(full + kCtStages);
@@ -330,8 +324,27 @@ k_confusion_tma(const LabelT *__restrict__ labels, const PredT *__restrict__ pre
     }
 }
 template <typename LabelT, typename PredT>
-static size_t confusion_tma_smem(int n_class) {
-    return (size_t)kCtStages * kCtChunk * (sizeof(LabelT) + sizeof(PredT)) + kCtStages * sizeof(u64) + (size_t)n_class * n_class * sizeof(u32);
+static size_t confusion_tma_smem(int n_class, int chunk, int stages) {
+    return (size_t)stages * chunk * (sizeof(LabelT) + sizeof(PredT)) + stages * sizeof(u64) + (size_t)n_class * n_class * sizeof(u32);
+}
+template <typename LabelT, typename PredT, int THREADS, int CHUNK, int STAGES>
+static int launch_confusion_tma(const LabelT *l, const PredT *p, long long n, int n_class, long long ignore, int has_ignore,
+                                unsigned long long *h, int max_classes, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    RTDA_RETURN_IF_CUDA_ERROR(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion_tma<LabelT, PredT, THREADS, CHUNK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)confusion_tma_smem<LabelT, PredT>(max_classes, CHUNK, STAGES)));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const long long chunks = (n + CHUNK - 1) / CHUNK;
+    long long tgrid = sm_count();
+    if (tgrid > chunks) tgrid = chunks;
+    k_confusion_tma<LabelT, PredT, THREADS, CHUNK, STAGES><<<(unsigned)tgrid, THREADS, confusion_tma_smem<LabelT, PredT>(n_class, CHUNK, STAGES), st>>>(
+        l, p, n, n_class, ignore, has_ignore, h);
+    RTDA_CHECK_LAUNCH();
+    return 0;
 }
 
 // Fused validation.py:95 (argmax over classes, first maximum wins) + the histogram.
@@ -401,25 +414,12 @@ static int launch_confusion(const void *labels, const void *preds, long long n, 
         const size_t ssm = (size_t)n_class * n_class * sizeof(u32);
 #if RTDA_CM_TMA
         // staged by bulk copies: 16-byte aligned maps (torch allocations are; a slice starting at an odd element is not)
-        // ... and several chunks per SM: on one 1024 x 2048 map (3.5 chunks per SM, 20 of the 148 blocks idle) it is no
-        // faster than k_confusion_stream (10.2-10.8 against 10.5 us), from 8 chunks per SM on it wins (8 maps: 42.5 against 47.7 us)
-        if (n_class <= kCtMaxClasses && ((uintptr_t)labels & 15) == 0 && ((uintptr_t)preds & 15) == 0 &&
-            n >= (long long)kCtChunk * 8 * sm_count()) {
-            const size_t tsm = confusion_tma_smem<LabelT, PredT>(n_class);
-            static bool attr_done[64] = {false};
-            int dev = 0;
-            RTDA_RETURN_IF_CUDA_ERROR(cudaGetDevice(&dev));
-            if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-                RTDA_RETURN_IF_CUDA_ERROR(cudaFuncSetAttribute(k_confusion_tma<LabelT, PredT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                               (int)confusion_tma_smem<LabelT, PredT>(kCtMaxClasses)));
-                if (dev >= 0 && dev < 64) attr_done[dev] = true;
-            }
-            const long long chunks = (n + kCtChunk - 1) / kCtChunk;
-            long long tgrid = sm_count();
-            if (tgrid > chunks) tgrid = chunks;
-            k_confusion_tma<LabelT, PredT><<<(unsigned)tgrid, kCtThreads, tsm, st>>>(l, p, n, n_class, ignore, has_ignore, h);
-            RTDA_CHECK_LAUNCH();
-            return 0;
+        if (((uintptr_t)labels & 15) == 0 && ((uintptr_t)preds & 15) == 0) {
+            // several 4096-pixel chunks per SM: the three-stage ring (8 maps per call: 42.5 us against 47.7 us of k_confusion_stream)
+            if (n_class <= kCtMaxClasses && n >= 4096ll * 8 * sm_count())
+                return launch_confusion_tma<LabelT, PredT, 1024, 4096, 3>(l, p, n, n_class, ignore, has_ignore, h, kCtMaxClasses, st);
+            // (one 1024 x 2048 map through a ring of seven 2048-pixel stages - 225.5 KB, its whole share of an SM in flight at
+            // once, nothing refilled - measured 10.3 us, as k_confusion_stream below: bytes in flight are not what one map waits for)
         }
 #endif
         if (ssm <= 40 * 1024 && ((uintptr_t)labels % (V * sizeof(LabelT))) == 0 && ((uintptr_t)preds % (V * sizeof(PredT))) == 0) {
