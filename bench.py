@@ -325,16 +325,17 @@ def measure_confusion(rank, dev, world, steps, warmup, batch=1, use_graph=True, 
     achieved = CM_BYTES_PER_PX * px / (per * 1e-3) / 1e9 if per > 0 else 0.0
     # calibration: what a plain device copy moving the SAME number of bytes reaches at this size (the measured
     # peak is a 2 GB transfer; a 33 MB one pays launch, ramp-up and tail like any kernel of a few microseconds)
+    # (one destination per source: a single 17 MB destination would stay in L2 and the copy would move half its bytes)
     src = [torch.empty(px, dtype=torch.int64, device=dev) for _ in range(n_sets)]
-    dst = torch.empty(px, dtype=torch.int64, device=dev)
-    for a in src:
-        dst.copy_(a)
+    dst = [torch.empty(px, dtype=torch.int64, device=dev) for _ in range(n_sets)]
+    for a, d in zip(src, dst):
+        d.copy_(a)
     cal_ms_graph = None
     try:
         gcal = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gcal):
-            for a in src:
-                dst.copy_(a)
+            for a, d in zip(src, dst):
+                d.copy_(a)
         ms_cal, _ = timed(lambda: [gcal.replay() for _ in range(4)], barrier, dev, world)
         cal_ms_graph = ms_cal / (4 * n_sets)
     except Exception:  # noqa: BLE001
