@@ -230,6 +230,8 @@ class Stepper:
     def _reduce(self, outs):
         import torch.distributed as dist
 
+        if os.environ.get("RTDA_BENCH_SKIP_ALLREDUCE"):  # measurement aid: what the per-step collective costs the local step
+            return
         if self.pending is not None:
             self.pending.wait()                      # stream-side wait; at most one collective in flight
         self.pending = dist.all_reduce(outs._view("packed"), op=dist.ReduceOp.SUM, async_op=True)
