@@ -75,3 +75,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.NativeLibraryError):
         _lib.load()
+
+
+def test_shapes_whose_finished_gradient_the_forward_writes(lib):
+    """rtda_lovasz_final_grad_supported (host logic only): per image always; global batches when the maps are a multiple
+    of 4096 pixels (a level-1 tile lies in one image) and C * B * HW fits the 30-bit pixel index of the sorted pairs."""
+    f = lib.rtda_lovasz_final_grad_supported
+    assert f(4, 19, 512 * 1024, 1) == 1 and f(16, 19, 720 * 1280, 1) == 1 and f(3, 19, 33 * 33, 1) == 1
+    assert f(1, 19, 33 * 47, 0) == 1                      # a batch of one is one image per group
+    assert f(4, 19, 512 * 1024, 0) == 1 and f(8, 19, 512 * 1024, 0) == 1 and f(2, 19, 64 * 64, 0) == 1
+    assert f(4, 19, 96 * 160, 0) == 0                     # 15360 pixels: not a multiple of 4096
+    assert f(4, 19, 33 * 33, 0) == 0
+    assert f(64, 19, 1024 * 1024, 0) == 0                 # 19 * 64 Mi elements do not fit the index field
+    assert f(0, 19, 4096, 0) == 0 and f(4, 0, 4096, 0) == 0
