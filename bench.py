@@ -403,10 +403,15 @@ def bench_confusion(args, rank, local_rank, world):
                 "h2d_bytes_per_step": px1 * 16, "d2h_bytes_per_step": 19 * 19 * 8,
                 "note": "rtda.fast_hist(label_true_np, label_pred_np, 19): pageable numpy maps -> H2D -> kernel -> 19x19 int64 D2H, wall clock"},
         "gpu_launches": m["kernel_launches"],
-        "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": m["peak"], "unit": "GB/s", "frac": m["frac"],
+        # one launch per step: the step time of the timed region (CUDA events around the replayed graph of back-to-back
+        # calls, launch gaps included) IS the kernel's average launch duration, as for the Lovasz line; the per-launch
+        # events of eager launches are kept beside it (they add ~3 us to a 10 us kernel, nothing to a 45 us one)
+        "roofline": {"bound": "hbm", "achieved": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9, "peak": m["peak"], "unit": "GB/s",
+                     "frac": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"],
                      "traffic": None, "peak_source": m["peak_src"], "dominant_kernel": "k_confusion",
-                     "ms_per_launch": m["kernel_ms"], "what": "16 B/px (int64 label + int64 prediction) x pixels per call / k_confusion CUDA-event time (two events around every eager launch)",
-                     "frac_graph_replay": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"],
+                     "ms_per_launch": m["ms_per_step"], "what": "16 B/px (int64 label + int64 prediction) x pixels per call / step time of the timed region (one k_confusion launch per step, " + m["launch"] + ")",
+                     "eager_events": {"ms_per_launch": m["kernel_ms"], "achieved": m["achieved"], "frac": m["frac"],
+                                      "what": "two CUDA events around every eager launch (library profile mode)"},
                      "plain_copy_of_the_same_bytes": {"ms": m["copy_same_bytes_ms"], "frac_of_peak": m["copy_same_bytes_frac"],
                                                       "what": "torch copy_ of the same number of bytes (read + write), graph-replayed back to back: the ceiling a kernel of this size can reach"}},
     }
@@ -752,8 +757,9 @@ def main():
                 secondary[f"c4_confusion_{batch}map"] = {
                     "workload": "c4: " + WORKLOADS["c4"][4], "maps_per_call": batch, "value": m["value"], "unit": "Mpix/s",
                     "ms_per_step": m["ms_per_step"], "launch": m["launch"], "kernel_ms_per_launch": m["kernel_ms"],
-                    "roofline_frac": m["frac"], "achieved_gbs_per_gpu": m["achieved"], "scaling": "weak",
-                    "roofline_frac_graph_replay": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"] / world * world,
+                    "roofline_frac": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9 / m["peak"],
+                    "achieved_gbs_per_gpu": CM_BYTES_PER_PX * m["px"] / (m["ms_per_step"] * 1e-3) / 1e9, "scaling": "weak",
+                    "roofline_frac_eager_events": m["frac"],
                     "plain_copy_of_the_same_bytes": {"ms": m["copy_same_bytes_ms"], "frac_of_peak": m["copy_same_bytes_frac"]}}
                 torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001
